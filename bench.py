@@ -1,0 +1,369 @@
+"""bench.py — headline benchmark of the SO-Net forward hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one eval-mode classifier forward (ModelNet40 shape: batch 64 per GPU, N=5000 points,
+8x8 SOM, k=3, som_k=9, fp32) over one batch of synthetic clouds. N>1: launched by torchrun, one
+rank per GPU, weights replicated, batch sharded (weak scaling), one NCCL all-gather of the logits
+per step inside the timed region. Rank 0 prints ONE JSON line.
+
+  value     clouds/s with inputs resident in HBM (CUDA events per step, L2 flushed between steps,
+            max over ranks)
+  e2e       the same metric through the public API classifier.Model.set_input()/test_model() with
+            pinned HOST buffers: H2D of every input and D2H of the logits inside the timed region
+  roofline  dominant kernel (by measured device time) vs MEASURED_PEAKS.json, measured live with
+            CUDA events around every C-ABI call of instrumented steps; `kernels` lists all of them
+  cpu_baseline   the oracle port of the reference's PyTorch-CPU path (oracle/oracle.py; the pool
+            runs in the reference's own compiled plugin when oracle/_ref exists) timed on this
+            box's host cores on a bounded sample
+  --impl reference   only that CPU arm, same JSON shape with "impl": "reference"
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "so-net_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "point-clouds/sec forward (ModelNet40 5000pt, 8x8 SOM)"
+UNIT = "clouds/s"
+B_PER_GPU, NPTS, M_NODES, SOM_K, K_NN, CLASSES = 64, 5000, 64, 9, 3, 40
+WORKLOAD = ("ModelNet40 classifier forward, batch=%d/GPU, N=%d pts, 8x8 SOM, k=%d, som_k=%d, "
+            "fp32, eval (BASELINE.json configs[1])" % (B_PER_GPU, NPTS, K_NN, SOM_K))
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            d["_source"] = "measured"
+            return d
+        except Exception:
+            pass
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback"
+    return d
+
+
+# ---- clocks sampling (B200_PROFILING.md recipe) -----------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ---- CPU arm: the oracle port of the reference path ----------------------------------------------------
+def cpu_arm(steps, warmup, sample_B=8):
+    """Time the oracle port (reference PyTorch-CPU dataflow) on the host cores."""
+    from oracle import build as obuild
+    obuild.build_c()
+    from oracle import oracle
+    from sonet_b200 import networks, synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    opt = synth.make_opt("classifier", batch_size=sample_B, input_pc_num=NPTS)
+    st_e = synth.synth_state_dict(networks.Encoder(opt), seed=1)
+    st_c = synth.synth_state_dict(networks.Classifier(opt), seed=2)
+    inp = synth.synth_inputs(sample_B, NPTS, seed=0)
+    kind = "port+reference-plugin" if oracle.ref_plugin() is not None else "port"
+
+    def step():
+        with torch.no_grad():
+            o = oracle.encoder_forward(st_e, opt, inp["pc"], inp["sn"], inp["node"],
+                                       inp["node_knn_I"], fast_pool=True)
+            return oracle.classifier_forward(st_c, o["feature"])
+
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    per = sum(times) / len(times)
+    return dict(value=sample_B / per, unit=UNIT, cores=torch.get_num_threads(),
+                kind="port", pool=kind, ms_per_step=per * 1e3,
+                sample="%d steps of a B=%d x N=%d classifier forward (oracle port of the "
+                       "reference PyTorch-CPU path; index_max via %s), after %d warm-up"
+                       % (steps, sample_B, NPTS,
+                          "the reference's compiled forward_multi_thread_cpu" if "plugin" in kind
+                          else "the C restatement", warmup))
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 2))
+    cb = cpu_arm(steps, warm)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "sample_batch": 8},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---- per-kernel roofline from instrumented steps -----------------------------------------------------
+def kernel_report(profile_steps, peaks):
+    """profile_steps: list of lists of (name, e0, e1, args). Returns per-call-site rows."""
+    rows = {}
+    order = []
+    for prof in profile_steps:
+        seen = {}
+        for name, e0, e1, a in prof:
+            ms = e0.elapsed_time(e1)
+            i = seen.get(name, 0)
+            seen[name] = i + 1
+            key = "%s#%d" % (name.replace("sonet_", ""), i)
+            if key not in rows:
+                rows[key] = dict(name=key, ms=[], args=a)
+                order.append(key)
+            rows[key]["ms"].append(ms)
+    out = []
+    hbm, tf = peaks["hbm_gbs"], peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    for key in order:
+        r = rows[key]
+        ms = sum(r["ms"]) / len(r["ms"])
+        a = r["args"]
+        row = {"kernel": key, "ms": round(ms, 4)}
+        if key.startswith("pointwise_layer"):
+            C0, C1, B, P, Cout = a[1], a[3], a[4], a[5], a[9]
+            flops = 2.0 * B * P * (C0 + C1) * Cout
+            ach = flops / (ms * 1e-3) / 1e12
+            row.update(bound="tensor", achieved=round(ach, 3), peak=tf, unit="TFLOP/s",
+                       frac=round(ach / tf, 5), shape="[%d,%d+%d,%d]->%d" % (B, C0, C1, P, Cout),
+                       note="fp32 CUDA-core path vs the bf16 tensor peak")
+        elif key.startswith("index_max"):
+            B, C, N, K = a[2], a[3], a[4], a[5]
+            byts = 4.0 * B * C * N + 4.0 * B * N + 4.0 * B * C * K * (2 if a[7] else 1)
+            ach = byts / (ms * 1e-3) / 1e9
+            row.update(bound="hbm", achieved=round(ach, 1), peak=hbm, unit="GB/s",
+                       frac=round(ach / hbm, 4), shape="[%d,%d,%d] K=%d" % (B, C, N, K))
+        elif key.startswith("som_mask"):
+            B, kN, M = a[1], a[2], a[3]
+            byts = 4.0 * B * kN * M + 4.0 * B * kN
+            ach = byts / (ms * 1e-3) / 1e9
+            row.update(bound="hbm", achieved=round(ach, 1), peak=hbm, unit="GB/s",
+                       frac=round(ach / hbm, 4))
+        out.append(row)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sonet_b200", choices=["sonet_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    from sonet_b200 import dist as sdist
+    rank, local_rank, world = sdist.env_world()
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference "
+                         "for the CPU arm")
+    rank, local_rank, world = sdist.init_from_env()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    import torch.distributed as dist
+    from sonet_b200 import _C, classifier, networks, ops, synth
+    _C.lib()
+    peaks = load_peaks()
+
+    B = B_PER_GPU
+    opt = synth.make_opt("classifier", batch_size=B, input_pc_num=NPTS, device=str(dev),
+                         gpu_id=dev.index)
+    cpu_opt = synth.make_opt("classifier", batch_size=B, input_pc_num=NPTS)
+    model = classifier.Model(opt)
+    model.encoder.load_state_dict(synth.synth_state_dict(networks.Encoder(cpu_opt), seed=1))
+    model.classifier.load_state_dict(synth.synth_state_dict(networks.Classifier(cpu_opt), seed=2))
+    inp = synth.synth_inputs(B, NPTS, seed=rank)            # each rank: its own shard
+    keys = ("pc", "sn", "label", "node", "node_knn_I")
+    host = [inp[k].pin_memory() for k in keys]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+    d2h_bytes = B * CLASSES * 4
+    total_rows = B * world
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gpu_step():
+        model.test_model()
+        return sdist.all_gather_rows(model.score, total_rows)
+
+    # ---- (1) device-resident arm -------------------------------------------------------------------
+    model.set_input(*host)
+    torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        gpu_step()
+    sampler = ClockSampler(dev.index)
+    barrier()
+    sampler.start()
+    l0 = ops.KERNEL_LAUNCHES
+    evs = []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()                                      # L2 flush, outside the event pair
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = gpu_step()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = ops.KERNEL_LAUNCHES - l0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    ms_per_step = total_ms / args.steps
+    value = total_rows * args.steps / (total_ms * 1e-3)
+
+    # ---- (2) end-to-end arm: host buffers through the public Model API ------------------------------
+    def e2e_step():
+        model.set_input(*host)                             # H2D (pinned, async on the stream)
+        model.test_model()
+        scores = sdist.all_gather_rows(model.score, total_rows)
+        return scores.cpu()                                # D2H + sync
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    t_e2e = []
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_step()
+        t_e2e.append(time.perf_counter() - t0)
+    barrier()
+    e2e_total = torch.tensor([sum(t_e2e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
+    e2e_value = total_rows * args.steps / float(e2e_total.item())
+    clocks = sampler.stop()
+
+    # ---- (3) instrumented steps: per-kernel device time with CUDA events ---------------------------
+    prof_steps = []
+    for _ in range(3):
+        flush.zero_()
+        ops.PROFILE = []
+        model.test_model()
+        torch.cuda.synchronize()
+        prof_steps.append(ops.PROFILE)
+        ops.PROFILE = None
+    kernels = kernel_report(prof_steps, peaks)
+    kernel_ms = sum(r["ms"] for r in kernels)
+    dom = max(kernels, key=lambda r: r["ms"])
+    # the dominant op family: the point-wise layers of the first PointResNet
+    pw = [r for r in kernels if r["kernel"].startswith("pointwise_layer")]
+    pw_ms = sum(r["ms"] for r in pw)
+    pw_flops = 0.0
+    for r in pw:
+        pw_flops += r["achieved"] * 1e12 * r["ms"] * 1e-3
+    tf_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    roofline = {"kernel": "pointwise_kernel (all %d 1x1-conv layers of the step)" % len(pw),
+                "bound": "tensor", "achieved": round(pw_flops / (pw_ms * 1e-3) / 1e12, 3),
+                "peak": tf_peak, "unit": "TFLOP/s",
+                "frac": round(pw_flops / (pw_ms * 1e-3) / 1e12 / tf_peak, 5),
+                "traffic": None, "peak_source": peaks["_source"] + " bf16 sustained",
+                "share_of_step": round(pw_ms / kernel_ms, 4),
+                "dominant_single_launch": dom["kernel"]}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_arm(steps=3, warmup=1)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": total_rows,
+                           "parallelism": "dp%d batch-sharded, 1 all-gather of logits/step" % world,
+                           "l2": "256 MB flush write between timed steps (outside event pairs)",
+                           "weights": "random (seeded), BN stats randomised"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": d2h_bytes * world},
+                "gpu_launches": launches, "wall_s_timed_region": round(wall, 4),
+                "clocks": clocks, "roofline": roofline, "kernels": kernels,
+                "cpu_baseline": cpu_baseline,
+                "checksum": float(out.double().sum().item())}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

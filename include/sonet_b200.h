@@ -1,0 +1,164 @@
+/*
+ * sonet_b200.h — C-ABI of libsonet_b200.so, the B200 (sm_100a) implementation of SO-Net's
+ * per-batch forward hot path.
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain device pointers + int dims + a trailing cudaStream_t (passed as void*
+ *     so that this header needs no CUDA include). No allocation, no synchronisation, no host
+ *     round-trip inside: every call is CUDA-graph capturable. The caller allocates outputs.
+ *   - All tensors are contiguous, channel-first, fp32 unless stated: [B, C, P] with P fastest.
+ *   - Return value: 0 = SONET_OK, negative = error; sonet_last_error_string() describes the
+ *     last error raised on the calling thread.
+ *   - Pointers marked "nullable" may be NULL to skip that output.
+ *
+ * Each function cites the reference interface (file:line under lijx10/SO-Net) it replaces.
+ */
+#ifndef SONET_B200_H_
+#define SONET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SONET_OK 0
+#define SONET_ERR_BAD_ARG (-1)
+#define SONET_ERR_CUDA (-2)
+#define SONET_ERR_UNSUPPORTED (-3)
+
+typedef void* sonet_stream_t; /* cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* sonet_last_error_string(void);
+/* "sonet_b200 <version> sm_100a" */
+const char* sonet_version(void);
+
+/* ---- a-6/a-7: per-node indexed arg-max pool ---------------------------------------------------
+ * Replaces index_max.forward_cuda / forward_cuda_shared_mem
+ *   (models/index_max_ext/index_max.cpp:132-148, index_max_cuda.cu:10-100; called at
+ *   models/networks.py:181-185).
+ * data [B,C,N] f32, index [B,N] i32 with values in [0,K) (validated only in debug builds; an
+ * out-of-range value is clamped, never a wild write), out_idx [B,C,K] i32:
+ *   out_idx[b,c,k] = lowest n with index[b,n]==k maximising data[b,c,n], provided that maximum
+ *   is > -1000.0f; otherwise 0 (empty node, or all values <= -1000: the reference's sentinel).
+ * out_val (nullable) [B,C,K] f32 = data[b,c,out_idx[b,c,k]]  — i.e. the masked gather of
+ *   models/networks.py:185 (first_pn_out_masked_max) fused into the pool.
+ * K <= 256 on the CUDA path. */
+int sonet_index_max_f32(const float* data, const int32_t* index, int B, int C, int N, int K,
+                        int32_t* out_idx, float* out_val, sonet_stream_t stream);
+
+/* Host (CPU) variants kept because the reference module exports them
+ * (index_max.forward_cpu / forward_multi_thread_cpu, index_max.cpp:33-112). They are API
+ * surface of the plugin, not a fallback: the CUDA entry points never route here. Host pointers. */
+int sonet_index_max_cpu_f32(const float* data, const int32_t* index, int B, int C, int N, int K,
+                            int32_t* out_idx, int thread_num);
+
+/* ---- a-1/a-2/a-3: SOM node <-> point assignment -------------------------------------------------
+ * Replaces BatchSOM.query_topk (util/som.py:237-269) plus the cluster statistics and centre
+ * lookup of Encoder.forward (models/networks.py:127-143, 168-172).
+ * x [B,3,N], node [B,3,M]  (M <= 256, 1 <= k <= 4, k <= M)
+ * Distances are ((dx*dx + dy*dy) + dz*dz) in fp32 without FMA contraction (bit-equal to the
+ * reference's ((x-node)**2).sum(1)); the k nearest nodes are emitted in ascending distance,
+ * lowest node index first on exact ties (the reference's topk(sorted=False) order is
+ * implementation-defined: parity is per-point set equality).
+ * Outputs:
+ *   min_idx_i32 [B,k*N]  slot-major: [slot0 for all n | slot1 ... ] (util/som.py:261-266)
+ *   min_idx_i64 [B,k*N]  nullable, same content as int64 (the dtype query_topk returns)
+ *   count       [B,M] i32  = mask_row_sum (models/networks.py:128)
+ *   row_max     [B,M] i32  = mask_row_max (count > 0)
+ *   cluster_mean[B,3,M] f32 = sum_{assigned copies} x / (count + 1e-5f)   (networks.py:140-142)
+ * The per-node sums are accumulated in a fixed order: results are bit-reproducible run to run
+ * and independent of how the batch is sharded across GPUs. */
+int sonet_som_assign(const float* x, const float* node, int B, int N, int M, int k,
+                     int32_t* min_idx_i32, int64_t* min_idx_i64, int32_t* count,
+                     int32_t* row_max, float* cluster_mean, sonet_stream_t stream);
+
+/* Dense one-hot mask of the assignment, util/som.py:255-265: mask[b, s*N+n, m] =
+ * (min_idx[b,s*N+n]==m), int32 [B,k*N,M]. Pure streaming write (HBM-bound). */
+int sonet_som_mask(const int32_t* min_idx_i32, int B, int kN, int M, int32_t* mask,
+                   sonet_stream_t stream);
+
+/* Centre lookup + decentre + concat, models/networks.py:168-172.
+ * centers[b,:,j] = cluster_mean[b,:,min_idx[b,j]] ; x_dec = x_stack - centers ;
+ * x_aug = cat(x_dec, sn_stack) where x_stack/sn_stack are x/sn repeated k times along points.
+ * x, sn [B,3,N] (sn nullable -> x_aug has 3 channels), outputs: centers [B,3,kN] (nullable),
+ * x_aug [B,3+3,kN] (channels 0-2 are x_decentered). */
+int sonet_som_decenter(const float* x, const float* sn, const float* cluster_mean,
+                       const int32_t* min_idx_i32, int B, int N, int M, int k,
+                       float* centers, float* x_aug, sonet_stream_t stream);
+
+/* ---- a-4/a-5/a-8/a-9/a-10: point-wise shared MLP layer (1x1 conv + folded BN + ReLU) ---------
+ * Replaces EquivariantLayer.forward / MyConv2d(1x1).forward in eval mode
+ * (models/layers.py:203-210, 282-296): out[b,co,p] = act(scale[co]*sum_ci W[co,ci]*X[b,ci,p] +
+ * shift[co] (+ addend[b,co,gidx[b,p]])), where X is the channel-concatenation of x0 [B,C0,P]
+ * and x1 [B,C1,P] (x1 nullable with C1=0) — the concat of PointResNet (layers.py:431) and of
+ * final_pointnet's input (networks.py:192) without materialising it.
+ * Wt [C0+C1, Cout] row-major = the conv weight TRANSPOSED (so that a K-slab of weights is
+ * contiguous along Cout), packed once by the host; scale/shift [Cout] hold conv bias and
+ * eval-mode BatchNorm folded by the host (scale nullable = 1; the host may also fold scale into
+ * Wt). relu: 0/1.
+ * addend (nullable) [B,Cout,G] with gidx [B,P] i32 in [0,G): per-point gathered additive term,
+ * used by the decomposed segmenter layer-1 (per-node and per-cloud channels).
+ * out [B,Cout,P]. (KNNModule's max over K, layers.py:365, is sonet_rowmax_f32 on the result.) */
+int sonet_pointwise_layer_f32(const float* x0, int C0, const float* x1, int C1, int B, int P,
+                              const float* Wt, const float* scale, const float* shift, int Cout,
+                              int relu, const float* addend, const int32_t* gidx, int G,
+                              float* out, sonet_stream_t stream);
+
+/* MyLinear in eval mode (models/layers.py:155-166): out[b,co] = act(scale*(W[co,:].x[b,:]) + shift)
+ * x [B,Cin], W [Cout,Cin], out [B,Cout]. */
+int sonet_linear_f32(const float* x, int B, int Cin, const float* W, const float* scale,
+                     const float* shift, int Cout, int relu, float* out, sonet_stream_t stream);
+
+/* max over the last dim: in [R, L] -> out [R] (global max over nodes, networks.py:197). */
+int sonet_rowmax_f32(const float* in, int R, int L, float* out, sonet_stream_t stream);
+
+/* ---- a-8: kNN gather on SOM nodes -----------------------------------------------------------------
+ * Replaces operations.knn_gather_wrapper / knn_gather_by_indexing (models/operations.py:19-54):
+ * out[b,c,m,j] = src[b,c,idx[b,m,j]],  src [B,C,M], idx [B,M,Kstride] i64 (first K columns
+ * used, as KNNModule slices precomputed_knn_I[:, :, 0:K], layers.py:332), out [B,C,M,K]. */
+int sonet_knn_gather_f32(const float* src, const int64_t* idx, int B, int C, int M, int K,
+                         int Kstride, float* out, sonet_stream_t stream);
+
+/* KNNModule input assembly (models/layers.py:346-361) in one pass:
+ * neighbours of node coordinates, their centre ('avg' = mean over K, 'center' = the node itself),
+ * decentred neighbours, gathered neighbour features, concatenated:
+ *   x_aug [B, 3+C, M*K], center [B,3,M].   center_type: 0 = 'avg', 1 = 'center'. */
+int sonet_knn_assemble_f32(const float* coord, const float* feat, const int64_t* idx, int B, int C,
+                           int M, int K, int Kstride, int center_type, float* center,
+                           float* x_aug, sonet_stream_t stream);
+
+/* Exact K-NN among the M nodes themselves (the precomputed_knn_I=None branch,
+ * models/layers.py:334-337): ascending distance, lowest index on ties. idx [B,M,K] i64. */
+int sonet_node_knn(const float* coord, int B, int M, int K, int64_t* idx, sonet_stream_t stream);
+
+/* Per-point gather of node features (models/segmenter.py:90-98):
+ * out[b,c,j] = src[b,c,gidx[b,j]], src [B,C,M], gidx [B,P] i32, out [B,C,P]. */
+int sonet_gather_points_f32(const float* src, const int32_t* gidx, int B, int C, int M, int P,
+                            float* out, sonet_stream_t stream);
+
+/* mean over the k stacked copies (models/networks.py:331-336): in [B,C,k*N] -> out [B,C,N],
+ * out = (1/k) * (in[...,0:N] + in[...,N:2N] (+ in[...,2N:3N])) in the reference's order. */
+int sonet_kcopy_mean_f32(const float* in, int B, int C, int N, int k, float* out,
+                         sonet_stream_t stream);
+
+/* ---- a-11: Chamfer distance ------------------------------------------------------------------------
+ * Replaces ChamferLoss.forward (models/losses.py:237-290) including the Faiss IndexFlatL2
+ * k=1 searches (losses.py:209-235) — exact brute force, direct differences, lowest index on ties.
+ * pred [B,3,Mp], gt [B,3,N].
+ *   idx_fwd [B,Mp] i32 : NN of each predicted point in gt;   idx_bwd [B,N] i32: NN of each gt
+ *   point in pred  (either nullable)
+ *   elem_fwd [B,Mp], elem_bwd [B,N] f32 (required): sqrt(|nn - p|^2 + 1e-8) per point
+ *     (forward_loss_element / backward_loss_element, losses.py:281, 286)
+ *   loss_fwd_arr, loss_bwd_arr [B] f32: per-cloud means of the above
+ *   loss [3] f32: {forward_loss, backward_loss, forward_loss + backward_loss} (means over B).
+ * All reductions run in a fixed order (bit-reproducible). */
+int sonet_chamfer_f32(const float* pred, const float* gt, int B, int Mp, int N, int32_t* idx_fwd,
+                      int32_t* idx_bwd, float* elem_fwd, float* elem_bwd, float* loss_fwd_arr,
+                      float* loss_bwd_arr, float* loss, sonet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SONET_B200_H_ */

@@ -1,0 +1,90 @@
+"""ref_shims.py — TEST INFRASTRUCTURE. Import the UNMODIFIED reference (/root/reference) on CPU.
+
+Only usable in the build container (the GPU box has no /root/reference). Three shims, as
+established in SURVEY.md §0 / Appendix B:
+  1. empty stub modules for matplotlib / mpl_toolkits (imported but unused, models/networks.py:14-15);
+  2. a `faiss` stub whose IndexFlatL2 is an exact brute-force search (only ChamferLoss uses it);
+  3. module `index_max` = the reference's own plugin compiled in place (oracle/_ref), with
+     forward_cuda redirected to the reference's forward_cpu for CPU tensors.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+
+
+def available():
+    return os.path.isdir(os.path.join(REF, "models"))
+
+
+class _IndexFlatL2:
+    def __init__(self, d):
+        self.d = d
+        self.db = None
+
+    def add(self, x):
+        self.db = np.ascontiguousarray(x, dtype=np.float32)
+
+    def search(self, q, k):
+        q = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32))
+        db = torch.from_numpy(self.db)
+        d = ((q[:, None, :] - db[None, :, :]) ** 2).sum(dim=2)
+        D, I = torch.topk(d, k=k, dim=1, largest=False, sorted=True)
+        return D.numpy(), I.numpy()
+
+
+def install(use_ref_plugin=True):
+    """Register the shims and put the reference on sys.path. Returns the reference's modules."""
+    if not available():
+        raise RuntimeError("/root/reference is not present on this machine")
+    for name in ("matplotlib", "matplotlib.pyplot", "mpl_toolkits", "mpl_toolkits.mplot3d"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["mpl_toolkits.mplot3d"].Axes3D = object
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+
+    faiss = types.ModuleType("faiss")
+
+    class _Res:
+        def setTempMemoryFraction(self, f):
+            pass
+
+    class _Cfg:
+        device = 0
+
+    faiss.StandardGpuResources = _Res
+    faiss.GpuIndexFlatConfig = _Cfg
+    faiss.IndexFlatL2 = _IndexFlatL2
+    faiss.index_cpu_to_gpu = lambda res, dev, idx: idx
+    sys.modules["faiss"] = faiss
+
+    from . import oracle
+    plugin = oracle.ref_plugin() if use_ref_plugin else None
+    shim = types.ModuleType("index_max")
+    if plugin is not None:
+        shim.forward_cpu = plugin.forward_cpu
+        shim.forward_multi_thread_cpu = plugin.forward_multi_thread_cpu
+        shim.forward_cuda = lambda data, index, K: plugin.forward_cpu(data, index, K)
+        shim.forward_cuda_shared_mem = shim.forward_cuda
+        shim.is_reference_binary = True
+    else:
+        shim.forward_cpu = oracle.index_max
+        shim.forward_cuda = oracle.index_max
+        shim.forward_cuda_shared_mem = oracle.index_max
+        shim.is_reference_binary = False
+    sys.modules["index_max"] = shim
+
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import models.autoencoder as ref_autoencoder
+    import models.classifier as ref_classifier
+    import models.losses as ref_losses
+    import models.networks as ref_networks
+    import models.segmenter as ref_segmenter
+    import util.som as ref_som
+    return types.SimpleNamespace(classifier=ref_classifier, segmenter=ref_segmenter,
+                                 autoencoder=ref_autoencoder, networks=ref_networks,
+                                 losses=ref_losses, som=ref_som, index_max=shim)

@@ -1,0 +1,91 @@
+// common.cuh — shared helpers for libsonet_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sonet_b200.h"
+
+namespace sonet {
+
+// thread-local error string, set by SONET_FAIL / check_launch
+void set_error(const char* fmt, ...);
+
+#define SONET_FAIL(code, ...)        \
+  do {                               \
+    ::sonet::set_error(__VA_ARGS__); \
+    return (code);                   \
+  } while (0)
+
+#define SONET_REQUIRE(cond, ...)                         \
+  do {                                                   \
+    if (!(cond)) SONET_FAIL(SONET_ERR_BAD_ARG, __VA_ARGS__); \
+  } while (0)
+
+// to be called right after a kernel launch; does not synchronise.
+int check_launch(const char* what);
+
+inline cudaStream_t as_stream(sonet_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();           // cached multiprocessor count of the current device
+int max_smem_optin();     // cached max opt-in dynamic shared memory per block
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ldg_stream_f1(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier / bulk-copy (TMA 1-D) wrappers ------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA unit, SASS UBLKCP); size multiple of 16, 16B aligned.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+}  // namespace sonet

@@ -1,0 +1,258 @@
+// som.cu — SOM node <-> point assignment for sm_100a.
+//
+// Replaces BatchSOM.query_topk (util/som.py:237-269) and the dense-mask arithmetic that
+// Encoder.forward builds on top of it (models/networks.py:127-143, 168-172). The reference
+// materialises diff[B,3,N,M], dist[B,N,M], a [B,N,M,k] compare and two [B,3,kN,M] products
+// (~2 GB at B=64,N=5000); here the assignment is 12 B in + 4k B out per point and the cluster
+// statistics are reduced straight from the indices.
+//
+//  som_assign_kernel   thread per point: 64 nodes in smem (broadcast reads), distances in the
+//                      reference's exact rounding order ((dx*dx+dy*dy)+dz*dz, no FMA), register
+//                      top-k insertion (ascending distance, lowest node index on ties).
+//  som_stats_kernel    CTA per (cloud, node): counts and coordinate sums in a fixed order
+//                      (strided per-thread partials + fixed tree) -> bit-reproducible and
+//                      independent of batch sharding; cluster_mean = sum / (count + 1e-5f).
+//  som_mask_kernel     optional dense one-hot mask [B,kN,M] int32 (the API of query_topk):
+//                      pure 16-byte streaming stores.
+//  som_decenter_kernel centers / x_decentered / x_augmented (networks.py:168-172).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace sonet {
+
+constexpr int SOM_MAX_M = 256;
+constexpr int SOM_MAX_K = 4;
+
+template <int KK>
+__global__ void __launch_bounds__(256)
+    som_assign_kernel(const float* __restrict__ x, const float* __restrict__ node, int N, int M,
+                      int32_t* __restrict__ idx32, int64_t* __restrict__ idx64) {
+  __shared__ float4 snode[SOM_MAX_M];
+  const int b = blockIdx.y;
+  const float* nb = node + static_cast<size_t>(b) * 3 * M;
+  for (int m = threadIdx.x; m < M; m += blockDim.x)
+    snode[m] = make_float4(nb[m], nb[M + m], nb[2 * M + m], 0.f);
+  __syncthreads();
+
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* xb = x + static_cast<size_t>(b) * 3 * N;
+  const float px = xb[n], py = xb[N + n], pz = xb[2 * N + n];
+
+  float bd[KK];
+  int bi[KK];
+#pragma unroll
+  for (int s = 0; s < KK; ++s) {
+    bd[s] = __int_as_float(0x7f800000);  // +inf
+    bi[s] = s;
+  }
+#pragma unroll 4
+  for (int m = 0; m < M; ++m) {
+    const float4 q = snode[m];
+    const float dx = __fsub_rn(px, q.x), dy = __fsub_rn(py, q.y), dz = __fsub_rn(pz, q.z);
+    const float d =
+        __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    if (d < bd[KK - 1]) {  // strict: on exact ties the earlier (lower) node index stays
+      bd[KK - 1] = d;
+      bi[KK - 1] = m;
+#pragma unroll
+      for (int s = KK - 1; s > 0; --s) {
+        if (bd[s] < bd[s - 1]) {
+          const float td = bd[s];
+          bd[s] = bd[s - 1];
+          bd[s - 1] = td;
+          const int ti = bi[s];
+          bi[s] = bi[s - 1];
+          bi[s - 1] = ti;
+        }
+      }
+    }
+  }
+  const size_t o = static_cast<size_t>(b) * KK * N + n;
+#pragma unroll
+  for (int s = 0; s < KK; ++s) {
+    idx32[o + static_cast<size_t>(s) * N] = bi[s];
+    if (idx64 != nullptr) idx64[o + static_cast<size_t>(s) * N] = bi[s];
+  }
+}
+
+constexpr int STATS_THREADS = 256;
+
+__global__ void __launch_bounds__(STATS_THREADS)
+    som_stats_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx32, int N, int M,
+                     int k, int32_t* __restrict__ count, int32_t* __restrict__ row_max,
+                     float* __restrict__ cluster_mean) {
+  const int m = blockIdx.x, b = blockIdx.y;
+  const int kN = k * N;
+  const int32_t* ib = idx32 + static_cast<size_t>(b) * kN;
+  const float* xb = x + static_cast<size_t>(b) * 3 * N;
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  int cnt = 0;
+  // the stacked point order j = s*N + n is the reference's x_stack order (networks.py:132-137)
+  for (int j = threadIdx.x; j < kN; j += STATS_THREADS) {
+    if (ib[j] == m) {
+      int n = j;
+      while (n >= N) n -= N;
+      sx += xb[n];
+      sy += xb[N + n];
+      sz += xb[2 * N + n];
+      ++cnt;
+    }
+  }
+  __shared__ float rs[3][STATS_THREADS];
+  __shared__ int rc[STATS_THREADS];
+  rs[0][threadIdx.x] = sx;
+  rs[1][threadIdx.x] = sy;
+  rs[2][threadIdx.x] = sz;
+  rc[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int w = STATS_THREADS / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) {
+      rs[0][threadIdx.x] += rs[0][threadIdx.x + w];
+      rs[1][threadIdx.x] += rs[1][threadIdx.x + w];
+      rs[2][threadIdx.x] += rs[2][threadIdx.x + w];
+      rc[threadIdx.x] += rc[threadIdx.x + w];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int c = rc[0];
+    count[static_cast<size_t>(b) * M + m] = c;
+    row_max[static_cast<size_t>(b) * M + m] = c > 0 ? 1 : 0;
+    const float den = __fadd_rn(static_cast<float>(c), 1e-5f);
+    float* cm = cluster_mean + static_cast<size_t>(b) * 3 * M;
+    cm[m] = __fdiv_rn(rs[0][0], den);
+    cm[M + m] = __fdiv_rn(rs[1][0], den);
+    cm[2 * M + m] = __fdiv_rn(rs[2][0], den);
+  }
+}
+
+// mask[b, j, m] = (idx[b,j] == m): one thread writes 4 consecutive m as an int4.
+__global__ void __launch_bounds__(256)
+    som_mask_kernel(const int32_t* __restrict__ idx32, long long rows, int M,
+                    int32_t* __restrict__ mask) {
+  const int quads = M >> 2;  // M % 4 == 0 on this path
+  const long long total = rows * quads;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = t / quads;
+    const int q = static_cast<int>(t - r * quads);
+    const int id = __ldg(idx32 + r) - (q << 2);
+    int4 v = make_int4(id == 0, id == 1, id == 2, id == 3);
+    __stcs(reinterpret_cast<int4*>(mask + r * M) + q, v);
+  }
+}
+__global__ void __launch_bounds__(256)
+    som_mask_scalar_kernel(const int32_t* __restrict__ idx32, long long rows, int M,
+                           int32_t* __restrict__ mask) {
+  const long long total = rows * M;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = t / M;
+    mask[t] = (__ldg(idx32 + r) == static_cast<int>(t - r * M)) ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    som_decenter_kernel(const float* __restrict__ x, const float* __restrict__ sn,
+                        const float* __restrict__ cluster_mean, const int32_t* __restrict__ idx32,
+                        int N, int M, int k, float* __restrict__ centers,
+                        float* __restrict__ x_aug) {
+  extern __shared__ float scm[];  // [3][M]
+  const int b = blockIdx.y;
+  const float* cm = cluster_mean + static_cast<size_t>(b) * 3 * M;
+  for (int i = threadIdx.x; i < 3 * M; i += blockDim.x) scm[i] = cm[i];
+  __syncthreads();
+  const int kN = k * N;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= kN) return;
+  int n = j;
+  while (n >= N) n -= N;
+  int id = idx32[static_cast<size_t>(b) * kN + j];
+  id = min(max(id, 0), M - 1);
+  const float* xb = x + static_cast<size_t>(b) * 3 * N;
+  const int CA = sn ? 6 : 3;
+  float* ab = x_aug + static_cast<size_t>(b) * CA * kN;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float ctr = scm[c * M + id];
+    if (centers) centers[(static_cast<size_t>(b) * 3 + c) * kN + j] = ctr;
+    ab[static_cast<size_t>(c) * kN + j] = __fsub_rn(xb[c * N + n], ctr);
+  }
+  if (sn) {
+    const float* sb = sn + static_cast<size_t>(b) * 3 * N;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ab[static_cast<size_t>(3 + c) * kN + j] = sb[c * N + n];
+  }
+}
+
+}  // namespace sonet
+
+extern "C" int sonet_som_assign(const float* x, const float* node, int B, int N, int M, int k,
+                                int32_t* min_idx_i32, int64_t* min_idx_i64, int32_t* count,
+                                int32_t* row_max, float* cluster_mean, sonet_stream_t stream) {
+  using namespace sonet;
+  SONET_REQUIRE(B >= 0 && N >= 0, "som_assign: negative dimension");
+  SONET_REQUIRE(M >= 1 && M <= SOM_MAX_M, "som_assign: M=%d out of range [1,%d]", M, SOM_MAX_M);
+  SONET_REQUIRE(k >= 1 && k <= SOM_MAX_K && k <= M, "som_assign: k=%d out of range", k);
+  SONET_REQUIRE(B <= 65535, "som_assign: B=%d exceeds grid limit", B);
+  if (B == 0) return SONET_OK;
+  SONET_REQUIRE(x && node && min_idx_i32, "som_assign: null pointer");
+  SONET_REQUIRE((count && row_max && cluster_mean) || (!count && !row_max && !cluster_mean),
+                "som_assign: count/row_max/cluster_mean must be all set or all null");
+  cudaStream_t st = as_stream(stream);
+  if (N > 0) {
+    dim3 grid((N + 255) / 256, B);
+    switch (k) {
+      case 1: som_assign_kernel<1><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64); break;
+      case 2: som_assign_kernel<2><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64); break;
+      case 3: som_assign_kernel<3><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64); break;
+      default: som_assign_kernel<4><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64); break;
+    }
+    int rc = check_launch("som_assign");
+    if (rc) return rc;
+  }
+  if (count) {
+    som_stats_kernel<<<dim3(M, B), STATS_THREADS, 0, st>>>(x, min_idx_i32, N, M, k, count, row_max,
+                                                          cluster_mean);
+    return check_launch("som_stats");
+  }
+  return SONET_OK;
+}
+
+extern "C" int sonet_som_mask(const int32_t* min_idx_i32, int B, int kN, int M, int32_t* mask,
+                              sonet_stream_t stream) {
+  using namespace sonet;
+  SONET_REQUIRE(B >= 0 && kN >= 0 && M >= 1, "som_mask: bad dimension");
+  const long long rows = static_cast<long long>(B) * kN;
+  if (rows == 0) return SONET_OK;
+  SONET_REQUIRE(min_idx_i32 && mask, "som_mask: null pointer");
+  cudaStream_t st = as_stream(stream);
+  const int sms = sm_count();
+  if (M % 4 == 0 && aligned16(mask)) {
+    const long long total = rows * (M >> 2);
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 16LL * sms));
+    som_mask_kernel<<<grid, 256, 0, st>>>(min_idx_i32, rows, M, mask);
+  } else {
+    const long long total = rows * M;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 16LL * sms));
+    som_mask_scalar_kernel<<<grid, 256, 0, st>>>(min_idx_i32, rows, M, mask);
+  }
+  return check_launch("som_mask");
+}
+
+extern "C" int sonet_som_decenter(const float* x, const float* sn, const float* cluster_mean,
+                                  const int32_t* min_idx_i32, int B, int N, int M, int k,
+                                  float* centers, float* x_aug, sonet_stream_t stream) {
+  using namespace sonet;
+  SONET_REQUIRE(B >= 0 && N >= 0 && M >= 1 && k >= 1, "som_decenter: bad dimension");
+  SONET_REQUIRE(B <= 65535, "som_decenter: B=%d exceeds grid limit", B);
+  if (B == 0 || N == 0) return SONET_OK;
+  SONET_REQUIRE(x && cluster_mean && min_idx_i32 && x_aug, "som_decenter: null pointer");
+  const int kN = k * N;
+  dim3 grid((kN + 255) / 256, B);
+  som_decenter_kernel<<<grid, 256, 3 * M * sizeof(float), as_stream(stream)>>>(
+      x, sn, cluster_mean, min_idx_i32, N, M, k, centers, x_aug);
+  return check_launch("som_decenter");
+}

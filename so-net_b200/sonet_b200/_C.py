@@ -1,0 +1,80 @@
+"""ctypes binding of libsonet_b200.so (the C-ABI declared in include/sonet_b200.h).
+
+The library is the product: if it is missing, importing any op raises — there is NO Python/CPU
+fallback for the CUDA entry points. Tensors cross the boundary as raw device pointers; outputs
+are allocated by the caller (here, by the thin wrappers in ops.py with torch.empty).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsonet_b200.so")
+
+_lib = None
+
+c_int = ctypes.c_int
+c_void_p = ctypes.c_void_p
+
+# name -> argtypes (restype is always int unless listed in _RESTYPE)
+_SIGNATURES = {
+    "sonet_index_max_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                            c_void_p],
+    "sonet_index_max_cpu_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int],
+    "sonet_som_assign": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                         c_void_p, c_void_p, c_void_p, c_void_p],
+    "sonet_som_mask": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sonet_som_decenter": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                           c_void_p, c_void_p, c_void_p],
+    "sonet_pointwise_layer_f32": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
+                                  c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
+                                  c_void_p, c_void_p],
+    "sonet_linear_f32": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                         c_void_p, c_void_p],
+    "sonet_rowmax_f32": [c_void_p, c_int, c_int, c_void_p, c_void_p],
+    "sonet_knn_gather_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                             c_void_p],
+    "sonet_knn_assemble_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                               c_int, c_void_p, c_void_p, c_void_p],
+    "sonet_node_knn": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sonet_gather_points_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                c_void_p],
+    "sonet_kcopy_mean_f32": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sonet_chamfer_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sonet_last_error_string": [],
+    "sonet_version": [],
+}
+_RESTYPE = {"sonet_last_error_string": ctypes.c_char_p, "sonet_version": ctypes.c_char_p}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib():
+    """Load (once) and return the ctypes handle. Raises if the library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libsonet_b200.so not found at %s — build it with `python so-net_b200/build.py` "
+                "(there is no fallback path)" % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if a declared symbol is not exported
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPE.get(name, c_int)
+        _lib = handle
+    return _lib
+
+
+def last_error():
+    return lib().sonet_last_error_string().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, last_error()))
+
+
+def ptr(t):
+    """Device/host pointer of a tensor as an integer (None -> NULL)."""
+    return None if t is None else t.data_ptr()

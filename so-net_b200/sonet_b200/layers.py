@@ -1,0 +1,426 @@
+"""Layer classes with the reference's constructor signatures and state_dict keys
+(models/layers.py:22-432), running on the sm_100a kernels of libsonet_b200 in eval/no-grad mode.
+
+Dispatch rule (SURVEY.md §8b "Autograd"): the hand-written forward kernels are used whenever the
+module is in eval() mode and autograd is not recording (the metric: eval forward, torch.no_grad()).
+In train() mode, or when gradients are required, the layers compose differentiable PyTorch ops on
+the GPU exactly as the reference does — that is the reference's own training path, not a CPU
+fallback. Non-default options ('instance' norm, elu/swish/leakyrelu) always take the PyTorch path.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn.modules.batchnorm import _BatchNorm
+
+from . import operations, ops
+
+
+def _fast_ok(module, *tensors):
+    if module.training or torch.is_grad_enabled():
+        return False
+    return all(t is not None and t.is_cuda and t.dtype == torch.float32 for t in tensors)
+
+
+class Swish(nn.Module):
+    """x * sigmoid(x) (models/layers.py:14-19)."""
+
+    def forward(self, x):
+        return x * torch.sigmoid(x)
+
+
+class _MomentumDecayBatchNorm(_BatchNorm):
+    """BatchNorm whose momentum decays with the epoch (models/layers.py:22-70, 73-120)."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True,
+                 momentum_decay_step=None, momentum_decay=1):
+        super().__init__(num_features, eps, momentum, affine)
+        self.momentum_decay_step = momentum_decay_step
+        self.momentum_decay = momentum_decay
+        self.momentum_original = self.momentum
+
+    def forward(self, input, epoch=None):
+        step = self.momentum_decay_step
+        if epoch is not None and epoch >= 1 and step is not None and step > 0:
+            self.momentum = max(self.momentum_original * (self.momentum_decay ** (epoch // step)),
+                                0.01)
+        return F.batch_norm(input, self.running_mean, self.running_var, self.weight, self.bias,
+                            self.training, self.momentum, self.eps)
+
+
+class MyBatchNorm1d(_MomentumDecayBatchNorm):
+    def _check_input_dim(self, input):
+        if input.dim() not in (2, 3):
+            raise ValueError('expected 2D or 3D input (got {}D input)'.format(input.dim()))
+
+
+class MyBatchNorm2d(_MomentumDecayBatchNorm):
+    def _check_input_dim(self, input):
+        if input.dim() != 4:
+            raise ValueError('expected 4D input (got {}D input)'.format(input.dim()))
+
+
+def _make_act(activation):
+    if activation == 'relu':
+        return nn.ReLU()
+    if activation == 'elu':
+        return nn.ELU(alpha=1.0)
+    if activation == 'swish':
+        return Swish()
+    if activation == 'leakyrelu':
+        return nn.LeakyReLU(0.1)
+    return None
+
+
+class _FoldedParams:
+    """Eval-mode conv/linear + BatchNorm folded into (weights, shift), re-packed only when a
+    parameter or running statistic changes (tracked through tensor version counters).
+
+      y = gamma * (W x + bias - mean) / sqrt(var + eps) + beta  =  (s*W) x + ((bias-mean)*s + beta)
+    """
+
+    def __init__(self):
+        self._key = None
+        self.w = None       # conv layers: transposed [Cin, Cout]; linear: [Cout, Cin]
+        self.shift = None   # [Cout]
+
+    def get(self, weight2d, bias, norm, transpose):
+        srcs = [weight2d, bias]
+        if norm is not None:
+            srcs += [norm.weight, norm.bias, norm.running_mean, norm.running_var]
+        key = tuple((t.data_ptr(), t._version, t.device) for t in srcs if t is not None)
+        if key != self._key:
+            with torch.no_grad():
+                w = weight2d.detach().float()
+                shift = bias.detach().float() if bias is not None else \
+                    torch.zeros(w.shape[0], device=w.device)
+                if norm is not None:
+                    s = norm.weight.detach() / torch.sqrt(norm.running_var.detach() + norm.eps)
+                    shift = (shift - norm.running_mean.detach()) * s + norm.bias.detach()
+                    w = w * s[:, None]
+                self.w = (w.t() if transpose else w).contiguous()
+                self.shift = shift.contiguous()
+            self._key = key
+        return self.w, self.shift
+
+
+class MyLinear(nn.Module):
+    """Linear + BN1d + act (models/layers.py:123-166)."""
+
+    def __init__(self, in_features, out_features, activation=None, normalization=None,
+                 momentum=0.1, bn_momentum_decay_step=None, bn_momentum_decay=1):
+        super().__init__()
+        self.activation = activation
+        self.normalization = normalization
+        self.linear = nn.Linear(in_features, out_features, bias=True)
+        if normalization == 'batch':
+            self.norm = MyBatchNorm1d(out_features, momentum=momentum, affine=True,
+                                      momentum_decay_step=bn_momentum_decay_step,
+                                      momentum_decay=bn_momentum_decay)
+        elif normalization == 'instance':
+            self.norm = nn.InstanceNorm1d(out_features, momentum=momentum, affine=True)
+        act = _make_act(activation)
+        if act is not None:
+            self.act = act
+        self._folded = _FoldedParams()
+        self.weight_init()
+
+    def weight_init(self):
+        nn.init.normal_(self.linear.weight, 0, math.sqrt(2. / self.linear.in_features))
+        nn.init.zeros_(self.linear.bias)
+        if self.normalization in ('batch', 'instance'):
+            nn.init.ones_(self.norm.weight)
+            nn.init.zeros_(self.norm.bias)
+
+    def _fast(self, x):
+        return (_fast_ok(self, x) and x.dim() == 2
+                and self.normalization in (None, 'batch') and self.activation in (None, 'relu'))
+
+    def forward(self, x, epoch=None):
+        if self._fast(x):
+            w, shift = self._folded.get(self.linear.weight, self.linear.bias,
+                                        self.norm if self.normalization == 'batch' else None,
+                                        transpose=False)
+            return ops.linear(x.contiguous(), w, None, shift, self.activation == 'relu')
+        x = self.linear(x)
+        if self.normalization == 'batch':
+            x = self.norm(x, epoch)
+        elif self.normalization is not None:
+            x = self.norm(x)
+        if self.activation is not None:
+            x = self.act(x)
+        return x
+
+
+class _PointwiseConvBase(nn.Module):
+    """Shared eval fast path of the 1x1 conv layers: y = act(BN(conv1x1(cat(x0, x1))))."""
+
+    def _conv_weight2d(self):
+        w = self.conv.weight
+        return w.view(w.shape[0], w.shape[1])
+
+    def _fast_eligible(self):
+        ks = self.conv.kernel_size
+        return (all(k == 1 for k in ks) and all(s == 1 for s in self.conv.stride)
+                and all(p == 0 for p in self.conv.padding)
+                and self.normalization in (None, 'batch') and self.activation in (None, 'relu'))
+
+    def forward_points(self, x0, x1=None, addend=None, gidx=None):
+        """x0 [B,C0,P] (+ x1 [B,C1,P] virtually concatenated on channels) -> [B,Cout,P]."""
+        w, shift = self._folded.get(self._conv_weight2d(), self.conv.bias,
+                                    self.norm if self.normalization == 'batch' else None,
+                                    transpose=True)
+        return ops.pointwise_layer(x0, w, None, shift, self.activation == 'relu', x1=x1,
+                                   addend=addend, gidx=gidx)
+
+
+class MyConv2d(_PointwiseConvBase):
+    """Conv2d + BN2d + act (models/layers.py:169-211); 1x1 kernels run on the point-wise kernel."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=True,
+                 activation=None, momentum=0.1, normalization=None, bn_momentum_decay_step=None,
+                 bn_momentum_decay=1):
+        super().__init__()
+        self.activation = activation
+        self.normalization = normalization
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, bias=bias)
+        if normalization == 'batch':
+            self.norm = MyBatchNorm2d(out_channels, momentum=momentum, affine=True,
+                                      momentum_decay_step=bn_momentum_decay_step,
+                                      momentum_decay=bn_momentum_decay)
+        elif normalization == 'instance':
+            self.norm = nn.InstanceNorm2d(out_channels, momentum=momentum, affine=True)
+        act = _make_act(activation)
+        if act is not None:
+            self.act = act
+        self._folded = _FoldedParams()
+        self.weight_init()
+
+    def weight_init(self):
+        c = self.conv
+        n = c.kernel_size[0] * c.kernel_size[1] * c.in_channels
+        nn.init.normal_(c.weight, 0, math.sqrt(2. / n))
+        if c.bias is not None:
+            nn.init.zeros_(c.bias)
+        if self.normalization in ('batch', 'instance'):
+            nn.init.ones_(self.norm.weight)
+            nn.init.zeros_(self.norm.bias)
+
+    def forward(self, x, epoch=None):
+        if _fast_ok(self, x) and x.dim() == 4 and self._fast_eligible():
+            B, C, H, W = x.shape
+            y = self.forward_points(x.contiguous().view(B, C, H * W))
+            return y.view(B, y.shape[1], H, W)
+        x = self.conv(x)
+        if self.normalization == 'batch':
+            x = self.norm(x, epoch)
+        elif self.normalization is not None:
+            x = self.norm(x)
+        if self.activation is not None:
+            x = self.act(x)
+        return x
+
+
+class UpConv(nn.Module):
+    """Nearest x2 upsample + 3x3 conv (models/layers.py:214-240); decoder only — PyTorch/cuDNN
+    (out of the hot-path scope)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=0,
+                 output_padding=0, bias=True, activation=None, normalization=None):
+        super().__init__()
+        self.activation = activation
+        self.normalization = normalization
+        self.up_sample = nn.Upsample(scale_factor=2)
+        self.conv = MyConv2d(in_channels, out_channels, kernel_size=3, stride=1, padding=1,
+                             bias=True, activation=activation, normalization=normalization)
+        self.weight_init()
+
+    def weight_init(self):
+        c = self.conv.conv
+        n = c.kernel_size[0] * c.kernel_size[1] * c.out_channels
+        nn.init.normal_(c.weight, 0, math.sqrt(2. / n))
+        if c.bias is not None:
+            nn.init.constant_(c.bias, 0.001)
+
+    def forward(self, x):
+        return self.conv(self.up_sample(x))
+
+
+class EquivariantLayer(_PointwiseConvBase):
+    """Conv1d(k=1) + BN1d + act on [B,C,P] (models/layers.py:243-296)."""
+
+    def __init__(self, num_in_channels, num_out_channels, activation='relu', normalization=None,
+                 momentum=0.1, bn_momentum_decay_step=None, bn_momentum_decay=1):
+        super().__init__()
+        self.num_in_channels = num_in_channels
+        self.num_out_channels = num_out_channels
+        self.activation = activation
+        self.normalization = normalization
+        self.conv = nn.Conv1d(num_in_channels, num_out_channels, kernel_size=1, stride=1,
+                              padding=0)
+        if normalization == 'batch':
+            self.norm = MyBatchNorm1d(num_out_channels, momentum=momentum, affine=True,
+                                      momentum_decay_step=bn_momentum_decay_step,
+                                      momentum_decay=bn_momentum_decay)
+        elif normalization == 'instance':
+            self.norm = nn.InstanceNorm1d(num_out_channels, momentum=momentum, affine=True)
+        act = _make_act(activation)
+        if act is not None:
+            self.act = act
+        self._folded = _FoldedParams()
+        self.weight_init()
+
+    def weight_init(self):
+        nn.init.normal_(self.conv.weight, 0,
+                        math.sqrt(2. / (self.conv.kernel_size[0] * self.conv.in_channels)))
+        if self.conv.bias is not None:
+            nn.init.zeros_(self.conv.bias)
+        if self.normalization in ('batch', 'instance'):
+            nn.init.ones_(self.norm.weight)
+            nn.init.zeros_(self.norm.bias)
+
+    def fast(self, *tensors):
+        return _fast_ok(self, *tensors) and self._fast_eligible()
+
+    def forward(self, x, epoch=None):
+        if self.fast(x) and x.dim() == 3:
+            return self.forward_points(x.contiguous())
+        y = self.conv(x)
+        if self.normalization == 'batch':
+            y = self.norm(y, epoch)
+        elif self.normalization is not None:
+            y = self.norm(y)
+        if self.activation is not None:
+            y = self.act(y)
+        return y
+
+
+class KNNModule(nn.Module):
+    """Group K neighbour nodes, decentre, 1x1-conv stack, max over K (models/layers.py:299-367)."""
+
+    def __init__(self, in_channels, out_channels_list, activation, normalization, momentum=0.1,
+                 bn_momentum_decay_step=None, bn_momentum_decay=1):
+        super().__init__()
+        self.layers = nn.ModuleList()
+        prev = in_channels
+        for c_out in out_channels_list:
+            self.layers.append(MyConv2d(prev, c_out, kernel_size=1, stride=1, padding=0, bias=True,
+                                        activation=activation, normalization=normalization,
+                                        momentum=momentum,
+                                        bn_momentum_decay_step=bn_momentum_decay_step,
+                                        bn_momentum_decay=bn_momentum_decay))
+            prev = c_out
+
+    def forward(self, coordinate, x, precomputed_knn_I, K, center_type, epoch=None):
+        """coordinate [B,3,M], x [B,C,M], precomputed_knn_I [B,M,K'] -> (center [B,3,M],
+        feature [B,Cout,M])."""
+        fast = (_fast_ok(self, coordinate, x) and center_type in ('avg', 'center')
+                and all(l._fast_eligible() for l in self.layers)
+                and (precomputed_knn_I is None or precomputed_knn_I.is_cuda))
+        if fast:
+            coord = coordinate.detach().contiguous()
+            if precomputed_knn_I is not None:
+                assert precomputed_knn_I.size()[2] >= K
+                knn_I = precomputed_knn_I.contiguous()  # kernel reads the first K columns
+            else:
+                knn_I = ops.node_knn(coord, K)
+            B, C, M = x.shape
+            center, h = ops.knn_assemble(coord, x.contiguous(), knn_I, K, center_type)
+            for layer in self.layers:
+                h = layer.forward_points(h)                     # [B, C', M*K]
+            feature = ops.rowmax(h.view(B, h.shape[1], M, K))   # max over K
+            return center, feature
+
+        coordinate_tensor = coordinate.data
+        if precomputed_knn_I is not None:
+            assert precomputed_knn_I.size()[2] >= K
+            knn_I = precomputed_knn_I[:, :, 0:K]
+        else:
+            d = torch.sum((coordinate_tensor.unsqueeze(3) - coordinate_tensor.unsqueeze(2)) ** 2,
+                          dim=1)
+            _, knn_I = torch.topk(d, k=K, dim=2, largest=False, sorted=True)
+        neighbors = operations.knn_gather_wrapper(coordinate_tensor, knn_I)  # Bx3xMxK
+        if center_type == 'avg':
+            neighbors_center = torch.mean(neighbors, dim=3, keepdim=True)
+        elif center_type == 'center':
+            neighbors_center = coordinate_tensor.unsqueeze(3)
+        neighbors_decentered = (neighbors - neighbors_center).detach()
+        neighbors_center = neighbors_center.squeeze(3).detach()
+        x_neighbors = operations.knn_gather_by_indexing(x, knn_I)
+        x_augmented = torch.cat((neighbors_decentered, x_neighbors), dim=1)
+        for layer in self.layers:
+            x_augmented = layer(x_augmented, epoch)
+        feature, _ = torch.max(x_augmented, dim=3, keepdim=False)
+        return neighbors_center, feature
+
+
+def _chain(in_channels, out_channels_list, activation, normalization, momentum,
+           bn_momentum_decay_step, bn_momentum_decay, last_extra_in=0):
+    layers = nn.ModuleList()
+    prev = in_channels
+    last = len(out_channels_list) - 1
+    for i, c_out in enumerate(out_channels_list):
+        if i != last:
+            layers.append(EquivariantLayer(prev, c_out, activation, normalization, momentum,
+                                           bn_momentum_decay_step, bn_momentum_decay))
+        else:
+            layers.append(EquivariantLayer(prev + last_extra_in, c_out, None, None))
+        prev = c_out
+    return layers
+
+
+class PointNet(nn.Module):
+    """Chain of EquivariantLayers, last one bare (models/layers.py:370-387)."""
+
+    def __init__(self, in_channels, out_channels_list, activation, normalization, momentum=0.1,
+                 bn_momentum_decay_step=None, bn_momentum_decay=1):
+        super().__init__()
+        self.layers = _chain(in_channels, out_channels_list, activation, normalization, momentum,
+                             bn_momentum_decay_step, bn_momentum_decay)
+
+    def forward(self, x, epoch=None):
+        for layer in self.layers:
+            x = layer(x, epoch)
+        return x
+
+    def forward_pair(self, x0, x1, epoch=None):
+        """forward(torch.cat((x0, x1), dim=1)) without materialising the concat in eval mode."""
+        first = self.layers[0]
+        if first.fast(x0, x1):
+            x = first.forward_points(x0.contiguous(), x1.contiguous())
+            for layer in self.layers[1:]:
+                x = layer(x, epoch)
+            return x
+        return self.forward(torch.cat((x0, x1), dim=1), epoch)
+
+
+class PointResNet(nn.Module):
+    """in -> out[0] -> ... -> out[k-2]; cat(out[0], out[k-2]) -> out[k-1] (models/layers.py:390-432)."""
+
+    def __init__(self, in_channels, out_channels_list, activation, normalization, momentum=0.1,
+                 bn_momentum_decay_step=None, bn_momentum_decay=1):
+        super().__init__()
+        self.out_channels_list = out_channels_list
+        self.layers = _chain(in_channels, out_channels_list, activation, normalization, momentum,
+                             bn_momentum_decay_step, bn_momentum_decay,
+                             last_extra_in=out_channels_list[0])
+
+    def forward(self, x, epoch=None, x1=None):
+        """x [B,C,P]; x1: optional second tensor virtually concatenated to x (eval fast path)."""
+        n = len(self.out_channels_list)
+        first, last = self.layers[0], self.layers[n - 1]
+        if first.fast(x) and x.dim() == 3 and all(l.fast(x) for l in self.layers):
+            layer0_out = first.forward_points(x.contiguous(),
+                                              None if x1 is None else x1.contiguous())
+            x_tmp = layer0_out
+            for l in range(1, n - 1):
+                x_tmp = self.layers[l].forward_points(x_tmp)
+            return last.forward_points(layer0_out, x_tmp)   # the skip-concat, never materialised
+        if x1 is not None:
+            x = torch.cat((x, x1), dim=1)
+        layer0_out = first(x, epoch)
+        x_tmp = layer0_out
+        for l in range(1, n - 1):
+            x_tmp = self.layers[l](x_tmp, epoch)
+        return last(torch.cat((layer0_out, x_tmp), dim=1), epoch)

@@ -1,0 +1,257 @@
+"""Tensor-level wrappers over the C-ABI: validate, allocate outputs, pass the current stream.
+
+Every function here launches hand-written sm_100a kernels from libsonet_b200.so on the tensors'
+device and the current torch stream. Inputs must be CUDA, contiguous, of the stated dtype — the
+same checks the reference plugin does with CHECK_INPUT (models/index_max_ext/index_max.cpp:119-121),
+raised as RuntimeError. Nothing here falls back to PyTorch or the CPU.
+"""
+import torch
+
+from . import _C
+
+LAUNCHES = 0          # C-ABI compute calls issued
+KERNEL_LAUNCHES = 0   # CUDA kernels launched by those calls (bench.py's gpu_launches)
+_KERNELS_PER_CALL = {"sonet_som_assign": 2, "sonet_chamfer_f32": 4}
+PROFILE = None        # when a list: every call appends (name, start_event, end_event)
+
+
+def _chk(t, name, dtype=None, optional=False):
+    if t is None:
+        if optional:
+            return
+        raise RuntimeError("%s must not be None" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor/variable" % name)
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be contiguous" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError("%s must have dtype %s (got %s)" % (name, dtype, t.dtype))
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _call(name, *args):
+    global LAUNCHES, KERNEL_LAUNCHES
+    LAUNCHES += 1
+    KERNEL_LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
+    if PROFILE is None:
+        _C.check(getattr(_C.lib(), name)(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _C.check(getattr(_C.lib(), name)(*args), name)
+    e1.record()
+    PROFILE.append((name, e0, e1, args))
+
+
+def index_max(data, index, K, with_values=False):
+    """data [B,C,N] f32, index [B,N] i32 -> max_idx [B,C,K] i32 (and values [B,C,K] f32)."""
+    _chk(data, "data", torch.float32)
+    _chk(index, "index", torch.int32)
+    if data.dim() != 3 or index.dim() != 2 or index.shape[0] != data.shape[0] \
+            or index.shape[1] != data.shape[2]:
+        raise RuntimeError("index_max: expected data [B,C,N] and index [B,N], got %s and %s"
+                           % (tuple(data.shape), tuple(index.shape)))
+    B, C, N = data.shape
+    with torch.cuda.device(data.device):
+        out_idx = torch.empty((B, C, K), dtype=torch.int32, device=data.device)
+        out_val = torch.empty((B, C, K), dtype=torch.float32, device=data.device) \
+            if with_values else None
+        _call("sonet_index_max_f32", _C.ptr(data), _C.ptr(index), B, C, N, int(K),
+              _C.ptr(out_idx), _C.ptr(out_val), _stream(data))
+    return (out_idx, out_val) if with_values else out_idx
+
+
+def som_assign(x, node, k, want_i64=False, want_stats=True):
+    """x [B,3,N], node [B,3,M] -> dict(min_idx_i32 [B,kN], min_idx_i64?, count, row_max [B,M] i32,
+    cluster_mean [B,3,M])."""
+    _chk(x, "x", torch.float32)
+    _chk(node, "node", torch.float32)
+    if x.dim() != 3 or x.shape[1] != 3 or node.dim() != 3 or node.shape[1] != 3 \
+            or node.shape[0] != x.shape[0]:
+        raise RuntimeError("som_assign: expected x [B,3,N], node [B,3,M], got %s and %s"
+                           % (tuple(x.shape), tuple(node.shape)))
+    B, _, N = x.shape
+    M = node.shape[2]
+    dev = x.device
+    with torch.cuda.device(dev):
+        idx32 = torch.empty((B, k * N), dtype=torch.int32, device=dev)
+        idx64 = torch.empty((B, k * N), dtype=torch.int64, device=dev) if want_i64 else None
+        count = row_max = cmean = None
+        if want_stats:
+            count = torch.empty((B, M), dtype=torch.int32, device=dev)
+            row_max = torch.empty((B, M), dtype=torch.int32, device=dev)
+            cmean = torch.empty((B, 3, M), dtype=torch.float32, device=dev)
+        _call("sonet_som_assign", _C.ptr(x), _C.ptr(node), B, N, M, int(k), _C.ptr(idx32),
+              _C.ptr(idx64), _C.ptr(count), _C.ptr(row_max), _C.ptr(cmean), _stream(x))
+    return dict(min_idx_i32=idx32, min_idx_i64=idx64, count=count, row_max=row_max,
+                cluster_mean=cmean)
+
+
+def som_mask(min_idx_i32, M):
+    """min_idx [B,kN] i32 -> one-hot mask [B,kN,M] i32."""
+    _chk(min_idx_i32, "min_idx", torch.int32)
+    B, kN = min_idx_i32.shape
+    with torch.cuda.device(min_idx_i32.device):
+        mask = torch.empty((B, kN, M), dtype=torch.int32, device=min_idx_i32.device)
+        _call("sonet_som_mask", _C.ptr(min_idx_i32), B, kN, int(M), _C.ptr(mask),
+              _stream(min_idx_i32))
+    return mask
+
+
+def som_decenter(x, sn, cluster_mean, min_idx_i32, k, want_centers=False):
+    """-> (x_aug [B,3(+3),kN], centers [B,3,kN] or None)."""
+    _chk(x, "x", torch.float32)
+    _chk(sn, "sn", torch.float32, optional=True)
+    _chk(cluster_mean, "cluster_mean", torch.float32)
+    _chk(min_idx_i32, "min_idx", torch.int32)
+    B, _, N = x.shape
+    M = cluster_mean.shape[2]
+    kN = k * N
+    with torch.cuda.device(x.device):
+        x_aug = torch.empty((B, 6 if sn is not None else 3, kN), dtype=torch.float32,
+                            device=x.device)
+        centers = torch.empty((B, 3, kN), dtype=torch.float32, device=x.device) \
+            if want_centers else None
+        _call("sonet_som_decenter", _C.ptr(x), _C.ptr(sn), _C.ptr(cluster_mean),
+              _C.ptr(min_idx_i32), B, N, M, int(k), _C.ptr(centers), _C.ptr(x_aug), _stream(x))
+    return x_aug, centers
+
+
+def pointwise_layer(x0, Wt, scale, shift, relu, x1=None, addend=None, gidx=None, out=None):
+    """x0 [B,C0,P] (+ x1 [B,C1,P]) -> [B,Cout,P]; Wt [C0+C1,Cout] transposed folded weights."""
+    _chk(x0, "x0", torch.float32)
+    _chk(x1, "x1", torch.float32, optional=True)
+    _chk(Wt, "Wt", torch.float32)
+    _chk(scale, "scale", torch.float32, optional=True)
+    _chk(shift, "shift", torch.float32, optional=True)
+    _chk(addend, "addend", torch.float32, optional=True)
+    _chk(gidx, "gidx", torch.int32, optional=True)
+    B, C0, P = x0.shape
+    C1 = 0 if x1 is None else x1.shape[1]
+    if Wt.shape[0] != C0 + C1:
+        raise RuntimeError("pointwise_layer: Wt has %d input channels, inputs have %d"
+                           % (Wt.shape[0], C0 + C1))
+    Cout = Wt.shape[1]
+    G = 0 if addend is None else addend.shape[2]
+    with torch.cuda.device(x0.device):
+        if out is None:
+            out = torch.empty((B, Cout, P), dtype=torch.float32, device=x0.device)
+        _call("sonet_pointwise_layer_f32", _C.ptr(x0), C0, _C.ptr(x1), C1, B, P, _C.ptr(Wt),
+              _C.ptr(scale), _C.ptr(shift), Cout, int(bool(relu)), _C.ptr(addend), _C.ptr(gidx), G,
+              _C.ptr(out), _stream(x0))
+    return out
+
+
+def linear(x, W, scale, shift, relu):
+    """x [B,Cin], W [Cout,Cin] -> [B,Cout]."""
+    _chk(x, "x", torch.float32)
+    _chk(W, "W", torch.float32)
+    _chk(scale, "scale", torch.float32, optional=True)
+    _chk(shift, "shift", torch.float32, optional=True)
+    B, Cin = x.shape
+    Cout = W.shape[0]
+    with torch.cuda.device(x.device):
+        out = torch.empty((B, Cout), dtype=torch.float32, device=x.device)
+        _call("sonet_linear_f32", _C.ptr(x), B, Cin, _C.ptr(W), _C.ptr(scale), _C.ptr(shift),
+              Cout, int(bool(relu)), _C.ptr(out), _stream(x))
+    return out
+
+
+def rowmax(t):
+    """max over the last dim of a contiguous tensor."""
+    _chk(t, "input", torch.float32)
+    L = t.shape[-1]
+    R = t.numel() // max(L, 1)
+    with torch.cuda.device(t.device):
+        out = torch.empty(t.shape[:-1], dtype=torch.float32, device=t.device)
+        _call("sonet_rowmax_f32", _C.ptr(t), R, L, _C.ptr(out), _stream(t))
+    return out
+
+
+def knn_gather(src, idx, K=None):
+    """src [B,C,M], idx [B,M,K'] i64 -> [B,C,M,K]."""
+    _chk(src, "som_node", torch.float32)
+    _chk(idx, "som_node_knn_I", torch.int64)
+    B, C, M = src.shape
+    Kstride = idx.shape[2]
+    K = Kstride if K is None else K
+    with torch.cuda.device(src.device):
+        out = torch.empty((B, C, M, K), dtype=torch.float32, device=src.device)
+        _call("sonet_knn_gather_f32", _C.ptr(src), _C.ptr(idx), B, C, M, K, Kstride, _C.ptr(out),
+              _stream(src))
+    return out
+
+
+def knn_assemble(coord, feat, idx, K, center_type):
+    """-> (center [B,3,M], x_aug [B,3+C,M*K])."""
+    _chk(coord, "coordinate", torch.float32)
+    _chk(feat, "x", torch.float32)
+    _chk(idx, "knn_I", torch.int64)
+    B, C, M = feat.shape
+    Kstride = idx.shape[2]
+    ct = {"avg": 0, "center": 1}[center_type]
+    with torch.cuda.device(feat.device):
+        center = torch.empty((B, 3, M), dtype=torch.float32, device=feat.device)
+        x_aug = torch.empty((B, 3 + C, M * K), dtype=torch.float32, device=feat.device)
+        _call("sonet_knn_assemble_f32", _C.ptr(coord), _C.ptr(feat), _C.ptr(idx), B, C, M, int(K),
+              Kstride, ct, _C.ptr(center), _C.ptr(x_aug), _stream(feat))
+    return center, x_aug
+
+
+def node_knn(coord, K):
+    _chk(coord, "coordinate", torch.float32)
+    B, _, M = coord.shape
+    with torch.cuda.device(coord.device):
+        idx = torch.empty((B, M, K), dtype=torch.int64, device=coord.device)
+        _call("sonet_node_knn", _C.ptr(coord), B, M, int(K), _C.ptr(idx), _stream(coord))
+    return idx
+
+
+def gather_points(src, gidx):
+    """src [B,C,M], gidx [B,P] i32 -> [B,C,P]."""
+    _chk(src, "src", torch.float32)
+    _chk(gidx, "gidx", torch.int32)
+    B, C, M = src.shape
+    P = gidx.shape[1]
+    with torch.cuda.device(src.device):
+        out = torch.empty((B, C, P), dtype=torch.float32, device=src.device)
+        _call("sonet_gather_points_f32", _C.ptr(src), _C.ptr(gidx), B, C, M, P, _C.ptr(out),
+              _stream(src))
+    return out
+
+
+def kcopy_mean(t, k):
+    """[B,C,k*N] -> [B,C,N], mean of the k stacked copies."""
+    _chk(t, "input", torch.float32)
+    B, C, kN = t.shape
+    N = kN // k
+    with torch.cuda.device(t.device):
+        out = torch.empty((B, C, N), dtype=torch.float32, device=t.device)
+        _call("sonet_kcopy_mean_f32", _C.ptr(t), B, C, N, int(k), _C.ptr(out), _stream(t))
+    return out
+
+
+def chamfer(pred, gt, want_idx=False):
+    """pred [B,3,Mp], gt [B,3,N] -> dict(loss [3], fwd_arr [B], bwd_arr [B], elem_fwd, elem_bwd,
+    idx_fwd?, idx_bwd?)."""
+    _chk(pred, "predict_pc", torch.float32)
+    _chk(gt, "gt_pc", torch.float32)
+    B, _, Mp = pred.shape
+    N = gt.shape[2]
+    dev = pred.device
+    with torch.cuda.device(dev):
+        idx_f = torch.empty((B, Mp), dtype=torch.int32, device=dev) if want_idx else None
+        idx_b = torch.empty((B, N), dtype=torch.int32, device=dev) if want_idx else None
+        ef = torch.empty((B, Mp), dtype=torch.float32, device=dev)
+        eb = torch.empty((B, N), dtype=torch.float32, device=dev)
+        fa = torch.empty((B,), dtype=torch.float32, device=dev)
+        ba = torch.empty((B,), dtype=torch.float32, device=dev)
+        loss = torch.empty((3,), dtype=torch.float32, device=dev)
+        _call("sonet_chamfer_f32", _C.ptr(pred), _C.ptr(gt), B, Mp, N, _C.ptr(idx_f),
+              _C.ptr(idx_b), _C.ptr(ef), _C.ptr(eb), _C.ptr(fa), _C.ptr(ba), _C.ptr(loss),
+              _stream(pred))
+    return dict(loss=loss, fwd_arr=fa, bwd_arr=ba, elem_fwd=ef, elem_bwd=eb, idx_fwd=idx_f,
+                idx_bwd=idx_b)
