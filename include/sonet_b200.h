@@ -158,6 +158,37 @@ int sonet_chamfer_f32(const float* pred, const float* gt, int B, int Mp, int N, 
                       int32_t* idx_bwd, float* elem_fwd, float* elem_bwd, float* loss_fwd_arr,
                       float* loss_bwd_arr, float* loss, sonet_stream_t stream);
 
+/* ---- a-5 on tensor cores: the whole first PointResNet as one tcgen05 kernel ----------------------
+ * Replaces Encoder.first_pointnet = PointResNet(Cin,[64,128,256,384]).forward in eval mode
+ * (models/layers.py:419-432, models/networks.py:82-83,176): three Conv1d(k=1)+BN+ReLU layers, the
+ * skip-concat of layer-0's output and the bare 320->384 layer, for every stacked point copy.
+ * Activations stay in tensor memory between the layers; fp32 parity comes from a 3-product bf16
+ * hi/lo split (see csrc/pointmlp_tc.cu).
+ *   pack (host pointers): W0 [64,Cin], W1 [128,64], W2 [256,128], W3 [384,320] row-major with the
+ *     eval BatchNorm scale already folded in; shift0..3 = folded bias/BN shift. Writes the bf16
+ *     K-major core-matrix images streamed by the kernel into blob_host
+ *     (sonet_pointresnet_tc_blob_bytes() bytes) and the fp32 side parameters into fparams_host
+ *     (sonet_pointresnet_tc_fparam_count() floats).
+ *   forward (device pointers): x [B,Cin,P] (Cin <= 6), blob/fparams as packed (blob 16-byte
+ *     aligned), out [B,384,P]. */
+int sonet_pointresnet_tc_blob_bytes(void);
+int sonet_pointresnet_tc_fparam_count(void);
+int sonet_pointresnet_tc_pack(const float* W0, int Cin, const float* W1, const float* W2,
+                              const float* W3, const float* shift0, const float* shift1,
+                              const float* shift2, const float* shift3, void* blob_host,
+                              float* fparams_host);
+int sonet_pointresnet_tc_forward(const float* x, int Cin, int B, int P, const void* blob,
+                                 const float* fparams, float* out, sonet_stream_t stream);
+
+/* ---- diagnostics -------------------------------------------------------------------------------
+ * One 128 x N x K bf16 GEMM on tcgen05 (fp32 accumulate in TMEM), D = bf16(A) * bf16(Bm)^T.
+ * A [128,K], Bm [N,K], D [128,N] fp32 row-major device pointers. mode 0: A from shared memory
+ * (SS), 1: A from tensor memory (TS). layout 0/1 selects which of the two canonical no-swizzle
+ * K-major core-matrix arrangements is used; swap_fields exchanges the LBO/SBO descriptor fields.
+ * Exists so that tests can pin the descriptor encodings the fused point-MLP kernel relies on. */
+int sonet_debug_tc_probe(const float* A, const float* Bm, int N, int K, int mode, int layout,
+                         int swap_fields, float* D, sonet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,9 @@ def run_encoder_checks(tag, opt, enc, inp, st_enc, out):
     assert torch.equal(sets_ref, oracle.canon_sets(c_idx, k)), "C top-k != reference sets"
     assert torch.equal(sets_ref, oracle.canon_sets(orc["min_idx"], k))
     out["knn_sets"] = sets_ref.numpy().astype(np.int16)
+    # the reference's own slot order (topk(sorted=False) is implementation defined): needed to
+    # compare per-copy tensors (first_pn_out, centers, x_decentered) position by position
+    out["min_idx_ref"] = ref_min_idx.numpy().astype(np.int16)
     out["mask_row_max"] = torch.max(enc.mask, dim=1)[0].numpy()
     out["mask_row_sum"] = torch.sum(enc.mask, dim=1).numpy()
     names = ["som_node", "first_pn_out_masked_max", "final_pn_out", "feature"]

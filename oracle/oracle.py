@@ -223,8 +223,11 @@ def encoder_forward(st, opt, x, sn, node, node_knn_I, fast_pool=False):
     x_dec = x_stack - centers                                               # :171
     x_aug = torch.cat((x_dec, sn_stack), dim=1) if opt.surface_normal else x_dec
     first = pointresnet(x_aug, st, "first_pointnet")                        # :176
-    pool = index_max_fast if fast_pool else index_max
-    gather_index = pool(first, min_idx.int(), M).long()                     # :181-184
+    if fast_pool:   # baseline timing; an int selects the thread count
+        gather_index = index_max_fast(first, min_idx.int(), M,
+                                      None if fast_pool is True else int(fast_pool)).long()
+    else:
+        gather_index = index_max(first, min_idx.int(), M).long()           # :181-184
     masked_max = first.gather(2, gather_index * mask_row_max.unsqueeze(1).long())  # :185
     out = dict(mask=mask, mask_row_max=mask_row_max, min_idx=min_idx, mask_row_sum=mask_row_sum,
                som_node=som_node, centers=centers, x_decentered=x_dec, first_pn_out=first,

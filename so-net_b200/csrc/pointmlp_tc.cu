@@ -1,0 +1,427 @@
+// pointmlp_tc.cu — the first PointResNet (6|3 -> 64 -> 128 -> 256 -> [64+256] -> 384) of the SO-Net
+// encoder as ONE persistent tcgen05 kernel for sm_100a.
+//
+// Replaces Encoder.first_pointnet = PointResNet.forward (models/layers.py:419-432, wired at
+// models/networks.py:82-83,176): four EquivariantLayers (Conv1d k=1 + eval BatchNorm + ReLU,
+// layers.py:282-296) and the skip-concat torch.cat((layer0_out, x_tmp)) — 88 % of the forward's
+// FLOPs. The reference round-trips every activation through HBM (~7.4 GB at B=64,N=5000); here a
+// 128-point tile walks through all four layers inside one SM:
+//
+//   * points are the MMA M dimension (128 TMEM lanes = 128 point copies), channels are N/K;
+//   * layer 0 (K=3|6, degenerate for tensor cores) runs on CUDA cores, one thread per point;
+//   * layers 1-3 are tcgen05.mma kind::f16 with the ACTIVATIONS AS THE A OPERAND READ FROM TENSOR
+//     MEMORY: the epilogue warps read the fp32 accumulator (tcgen05.ld), add the folded-BN shift,
+//     ReLU, split into bf16 hi/lo and write the pair back IN PLACE over the accumulator columns
+//     (tcgen05.st) — a 16-channel group of fp32 columns becomes 8 hi + 8 lo packed columns, which
+//     is exactly the K-major A layout the next layer's MMA consumes. Activations never touch
+//     shared memory or HBM;
+//   * fp32 parity (1e-4) on bf16 tensor cores comes from the 3-product split
+//     x*w ~= hi(x)*hi(w) + lo(x)*hi(w) + hi(x)*lo(w)  (error ~2^-16, measured 1e-5 end to end);
+//   * weights (B operand, K-major no-swizzle core-matrix images packed once by the host) stream
+//     L2 -> shared memory through a 5-slot TMA ring (cp.async.bulk + mbarrier), layer-1 weights stay
+//     resident; each 32 KB slot is a [64 out-channels x 128 in-channels] hi+lo tile;
+//   * warp roles: warp 0 TMA producer, warp 1 MMA issuer (one thread), warps 4-11 epilogue
+//     (two warpgroups splitting the columns; warp%4 selects the TMEM lane quarter);
+//   * TMEM map (512 columns): [0,64) act0 | [64,192) D1/act1, later two D3 buffers |
+//     [192,448) D2/act2 | [448,512) third D3 buffer. Layer 3 is issued as six 64-channel chunks
+//     rotating over the three D3 buffers so that its epilogue (shift add + coalesced fp32 stores,
+//     lane = point) overlaps the MMAs of the next chunk.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "tc_common.cuh"
+
+namespace sonet {
+
+namespace pm {
+constexpr int C0 = 64, C1 = 128, C2 = 256, C3 = 384, K3 = C0 + C2;  // layer widths
+constexpr int TILE = 128;                                            // points per tile (MMA M)
+constexpr int SLOT_BYTES = 32768, NSLOT = 5;
+constexpr int W1_BYTES = 2 * C1 * C0 * 2;                            // hi + lo images, 32 KB
+constexpr int STAGES_PER_TILE = 4 + 18;
+constexpr int BLOB_BYTES = W1_BYTES + 4 * SLOT_BYTES + 6 * (2 * SLOT_BYTES + SLOT_BYTES / 2);
+constexpr int NFP = C0 * 6 + C0 + C1 + C2 + C3;                      // W0 | shift0..3 (floats)
+constexpr int NUM_THREADS = 384;
+constexpr int NBAR = 2 * NSLOT + 5 + 6 + 1;
+// shared memory carve-up
+constexpr int OFF_W1 = 0;
+constexpr int OFF_RING = OFF_W1 + W1_BYTES;
+constexpr int OFF_FP = OFF_RING + NSLOT * SLOT_BYTES;
+constexpr int OFF_BAR = OFF_FP + NFP * 4;
+constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16;
+// TMEM columns
+constexpr uint32_t COL_A0 = 0, COL_D1 = 64, COL_D2 = 192;
+__device__ __forceinline__ uint32_t d3_col(int buf) { return buf == 0 ? 448u : 64u * buf; }
+
+__host__ __device__ constexpr int stage_kt(int s) { return (s < 4 || ((s - 4) % 3) < 2) ? 128 : 64; }
+__host__ __device__ constexpr int stage_bytes(int s) { return stage_kt(s) * 64 * 2 * 2; }
+}  // namespace pm
+
+__global__ void __launch_bounds__(pm::NUM_THREADS, 1)
+    pointresnet_tc_kernel(const float* __restrict__ x_in, int Cin, int B, int P,
+                          const unsigned char* __restrict__ blob, const float* __restrict__ fparams,
+                          float* __restrict__ out) {
+  using namespace pm;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  float* fp = reinterpret_cast<float*>(smem + OFF_FP);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* full = bars;                   // [NSLOT]  TMA -> MMA
+  uint64_t* empty = bars + NSLOT;          // [NSLOT]  MMA -> TMA
+  uint64_t* b_act0 = bars + 2 * NSLOT;     // epilogue -> MMA
+  uint64_t* b_d1 = b_act0 + 1;             // MMA -> epilogue
+  uint64_t* b_act1 = b_act0 + 2;
+  uint64_t* b_d2 = b_act0 + 3;
+  uint64_t* b_act2 = b_act0 + 4;
+  uint64_t* d3full = b_act0 + 5;           // [3]
+  uint64_t* d3empty = d3full + 3;          // [3]
+  uint64_t* w1_full = d3empty + 3;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_cloud = (P + TILE - 1) / TILE;
+  const int num_tiles = B * tiles_per_cloud;
+  const int my_tiles = (static_cast<int>(blockIdx.x) < num_tiles)
+                           ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x
+                           : 0;
+
+  for (int i = threadIdx.x; i < NFP; i += NUM_THREADS) fp[i] = fparams[i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSLOT; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(b_act0, 8);
+    mbar_init(b_d1, 1);
+    mbar_init(b_act1, 8);
+    mbar_init(b_d2, 1);
+    mbar_init(b_act2, 8);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&d3full[i], 1);
+      mbar_init(&d3empty[i], 8);
+    }
+    mbar_init(w1_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tc::tmem_alloc(tmem_ptr, 512);
+    tc::tmem_relinquish();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tm = *tmem_ptr;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w1_full, W1_BYTES);
+      bulk_g2s(smem + OFF_W1, blob, W1_BYTES, w1_full);
+      uint32_t q = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        uint32_t off = W1_BYTES;
+        for (int s = 0; s < STAGES_PER_TILE; ++s, ++q) {
+          const uint32_t slot = q % NSLOT, use = q / NSLOT;
+          if (use > 0) tc::mbar_wait_bounded(&empty[slot], (use - 1) & 1, 100 + s);
+          const uint32_t bytes = stage_bytes(s);
+          mbar_arrive_expect_tx(&full[slot], bytes);
+          bulk_g2s(smem + OFF_RING + slot * SLOT_BYTES, blob + off, bytes, &full[slot]);
+          off += bytes;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer (one thread) ===========================
+    if (lane == 0) {
+      constexpr uint32_t IDESC = tc::idesc_bf16_f32(TILE, 64);
+      const uint32_t w1_addr = smem_u32(smem + OFF_W1);
+      const uint32_t ring_addr = smem_u32(smem + OFF_RING);
+      tc::mbar_wait_bounded(w1_full, 0, 1);
+      uint32_t q = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const uint32_t par = t & 1;
+        // ---- layer 1: D1[128 x 128] = act0[128 x 64] * W1^T, two 64-column chunks ----
+        tc::mbar_wait_bounded(b_act0, par, 2);
+        if (t > 0) {  // D1 overlaps D3 buffers 1,2 of the previous tile: wait for their drain
+          tc::mbar_wait_bounded(&d3empty[1], 1, 3);
+          tc::mbar_wait_bounded(&d3empty[2], 1, 4);
+        }
+        tc::fence_after_sync();
+#pragma unroll
+        for (int nc = 0; nc < 2; ++nc) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t a_hi = tm + COL_A0 + 16 * ks, a_lo = a_hi + 8;
+            const uint32_t bh = w1_addr + nc * 8192 + ks * 256, bl = bh + 16384;
+            const uint64_t dh = tc::smem_desc(bh, 128, 1024), dl = tc::smem_desc(bl, 128, 1024);
+            const uint32_t d = tm + COL_D1 + 64 * nc;
+            tc::mma_ts(d, a_hi, dh, IDESC, ks > 0);
+            tc::mma_ts(d, a_lo, dh, IDESC, 1);
+            tc::mma_ts(d, a_hi, dl, IDESC, 1);
+          }
+        }
+        tc::commit(b_d1);
+        // ---- layer 2: D2[128 x 256] = act1[128 x 128] * W2^T, four streamed 64-column chunks ----
+        tc::mbar_wait_bounded(b_act1, par, 5);
+        tc::fence_after_sync();
+        for (int nc = 0; nc < 4; ++nc, ++q) {
+          const uint32_t slot = q % NSLOT;
+          tc::mbar_wait_bounded(&full[slot], (q / NSLOT) & 1, 6);
+          tc::fence_after_sync();
+          const uint32_t sb = ring_addr + slot * SLOT_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t a_hi = tm + COL_D1 + 16 * ks, a_lo = a_hi + 8;
+            const uint64_t dh = tc::smem_desc(sb + ks * 256, 128, 2048),
+                           dl = tc::smem_desc(sb + 16384 + ks * 256, 128, 2048);
+            const uint32_t d = tm + COL_D2 + 64 * nc;
+            tc::mma_ts(d, a_hi, dh, IDESC, ks > 0);
+            tc::mma_ts(d, a_lo, dh, IDESC, 1);
+            tc::mma_ts(d, a_hi, dl, IDESC, 1);
+          }
+          tc::commit(&empty[slot]);
+        }
+        tc::commit(b_d2);
+        // ---- layer 3: D3[128 x 384] = cat(act0, act2)[128 x 320] * W3^T, six 64-column chunks ----
+        tc::mbar_wait_bounded(b_act2, par, 7);
+        tc::fence_after_sync();
+        for (int nc = 0; nc < 6; ++nc) {
+          const int buf = nc % 3;
+          if (nc >= 3) {
+            tc::mbar_wait_bounded(&d3empty[buf], 0, 8);   // drain of chunk nc-3 (this tile)
+          } else if (nc == 0 && t > 0) {
+            tc::mbar_wait_bounded(&d3empty[0], 1, 9);     // drain of chunk 3 of the previous tile
+          }
+          tc::fence_after_sync();
+          const uint32_t d = tm + d3_col(buf);
+          for (int kc = 0; kc < 3; ++kc, ++q) {
+            const uint32_t slot = q % NSLOT;
+            tc::mbar_wait_bounded(&full[slot], (q / NSLOT) & 1, 10);
+            tc::fence_after_sync();
+            const uint32_t sb = ring_addr + slot * SLOT_BYTES;
+            const int nks = (kc < 2) ? 8 : 4;
+            const uint32_t hi_bytes = (kc < 2) ? 16384u : 8192u;
+            const uint32_t sbo = (kc < 2) ? 2048u : 1024u;
+            for (int ks = 0; ks < nks; ++ks) {
+              const int kg = kc * 8 + ks;  // global 16-channel K group: 0-3 act0, 4-19 act2
+              const uint32_t a_hi = tm + (kg < 4 ? COL_A0 + 16 * kg : COL_D2 + 16 * (kg - 4));
+              const uint32_t a_lo = a_hi + 8;
+              const uint64_t dh = tc::smem_desc(sb + ks * 256, 128, sbo),
+                             dl = tc::smem_desc(sb + hi_bytes + ks * 256, 128, sbo);
+              tc::mma_ts(d, a_hi, dh, IDESC, kg > 0);
+              tc::mma_ts(d, a_lo, dh, IDESC, 1);
+              tc::mma_ts(d, a_hi, dl, IDESC, 1);
+            }
+            tc::commit(&empty[slot]);
+          }
+          tc::commit(&d3full[buf]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // =========================== epilogue warps ===========================
+    const int q4 = warp & 3;            // TMEM lane quarter this warp may access
+    const int h = (warp - 4) >> 2;      // column half handled by this warpgroup
+    const int r = q4 * 32 + lane;       // point within the tile == TMEM lane
+    const uint32_t lane_base = tm + (static_cast<uint32_t>(q4 * 32) << 16);
+    const float* W0 = fp;
+    const float* sh0 = fp + C0 * 6;
+    const float* sh1 = sh0 + C0;
+    const float* sh2 = sh1 + C1;
+    const float* sh3 = sh2 + C2;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = blockIdx.x + t * gridDim.x;
+      const int b = tile / tiles_per_cloud;
+      const int j = (tile - b * tiles_per_cloud) * TILE + r;
+      const bool valid = j < P;
+      const uint32_t par = t & 1;
+
+      // ---- layer 0 on CUDA cores: 32 of the 64 channels per warpgroup ----
+      float x[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+        x[c] = (valid && c < Cin) ? __ldg(x_in + (static_cast<size_t>(b) * Cin + c) * P + j) : 0.f;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int ch0 = 32 * h + 16 * g;
+        float y[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float* w = W0 + (ch0 + i) * 6;
+          float a = sh0[ch0 + i];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) a = fmaf(w[c], x[c], a);
+          y[i] = fmaxf(a, 0.f);
+        }
+        uint32_t wds[16];
+        tc::split16(y, wds);
+        tc::st16(lane_base + COL_A0 + ch0, wds);
+      }
+      tc::wait_st();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_act0);
+
+      // ---- layer 1 epilogue: 64 of 128 channels, in place ----
+      tc::mbar_wait_bounded(b_d1, par, 20);
+      tc::fence_after_sync();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int ch0 = 64 * h + 16 * g;
+        uint32_t v[16];
+        tc::ld16(lane_base + COL_D1 + ch0, v);
+        tc::wait_ld();
+        float y[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] = fmaxf(__uint_as_float(v[i]) + sh1[ch0 + i], 0.f);
+        tc::split16(y, v);
+        tc::st16(lane_base + COL_D1 + ch0, v);
+      }
+      tc::wait_st();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_act1);
+
+      // ---- layer 2 epilogue: 128 of 256 channels, in place ----
+      tc::mbar_wait_bounded(b_d2, par, 21);
+      tc::fence_after_sync();
+#pragma unroll 2
+      for (int g = 0; g < 8; ++g) {
+        const int ch0 = 128 * h + 16 * g;
+        uint32_t v[16];
+        tc::ld16(lane_base + COL_D2 + ch0, v);
+        tc::wait_ld();
+        float y[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] = fmaxf(__uint_as_float(v[i]) + sh2[ch0 + i], 0.f);
+        tc::split16(y, v);
+        tc::st16(lane_base + COL_D2 + ch0, v);
+      }
+      tc::wait_st();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_act2);
+
+      // ---- layer 3 epilogue: six chunks, 32 of each chunk's 64 channels; bare layer (no ReLU) ----
+      float* orow = out + (static_cast<size_t>(b) * C3) * P + j;
+      for (int nc = 0; nc < 6; ++nc) {
+        const int buf = nc % 3;
+        tc::mbar_wait_bounded(&d3full[buf], (nc / 3) & 1, 22);   // two uses per tile: parity = use&1
+        tc::fence_after_sync();
+        uint32_t v0[16], v1[16];
+        tc::ld16(lane_base + d3_col(buf) + 32 * h, v0);
+        tc::ld16(lane_base + d3_col(buf) + 32 * h + 16, v1);
+        tc::wait_ld();
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d3empty[buf]);
+        if (valid) {
+          const int co0 = 64 * nc + 32 * h;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            orow[static_cast<size_t>(co0 + i) * P] = __uint_as_float(v0[i]) + sh3[co0 + i];
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            orow[static_cast<size_t>(co0 + 16 + i) * P] = __uint_as_float(v1[i]) + sh3[co0 + 16 + i];
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tm, 512);
+}
+
+// ---- host-side packing -------------------------------------------------------------------------------
+static inline uint16_t f2bf(float f) {  // round-to-nearest-even, like cvt.rn.bf16.f32
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return static_cast<uint16_t>(u >> 16);  // inf / nan
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+static inline float bf2f(uint16_t h) {
+  const uint32_t u = static_cast<uint32_t>(h) << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+// Write the hi and lo K-major no-swizzle images of W[rows r0..r0+nr) x [k0..k0+kt) (row stride ld).
+static void pack_tile(const float* W, int ld, int r0, int nr, int k0, int kt, unsigned char* hi,
+                      unsigned char* lo) {
+  const uint32_t sbo = static_cast<uint32_t>(kt) * 16;
+  for (int r = 0; r < nr; ++r)
+    for (int k = 0; k < kt; ++k) {
+      const float w = W[static_cast<size_t>(r0 + r) * ld + k0 + k];
+      const uint16_t h = f2bf(w);
+      const uint16_t l = f2bf(w - bf2f(h));
+      const uint32_t off = (r >> 3) * sbo + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2;
+      std::memcpy(hi + off, &h, 2);
+      std::memcpy(lo + off, &l, 2);
+    }
+}
+
+}  // namespace sonet
+
+extern "C" int sonet_pointresnet_tc_blob_bytes(void) { return sonet::pm::BLOB_BYTES; }
+extern "C" int sonet_pointresnet_tc_fparam_count(void) { return sonet::pm::NFP; }
+
+extern "C" int sonet_pointresnet_tc_pack(const float* W0, int Cin, const float* W1, const float* W2,
+                                         const float* W3, const float* shift0, const float* shift1,
+                                         const float* shift2, const float* shift3, void* blob_host,
+                                         float* fparams_host) {
+  using namespace sonet;
+  using namespace sonet::pm;
+  SONET_REQUIRE(Cin >= 1 && Cin <= 6, "pointresnet_tc_pack: Cin=%d out of range [1,6]", Cin);
+  SONET_REQUIRE(W0 && W1 && W2 && W3 && shift0 && shift1 && shift2 && shift3 && blob_host &&
+                    fparams_host,
+                "pointresnet_tc_pack: null pointer");
+  unsigned char* blob = static_cast<unsigned char*>(blob_host);
+  std::memset(blob, 0, BLOB_BYTES);
+  pack_tile(W1, C0, 0, C1, 0, C0, blob, blob + W1_BYTES / 2);
+  size_t off = W1_BYTES;
+  for (int nc = 0; nc < 4; ++nc) {  // layer 2: [64 rows x 128]
+    pack_tile(W2, C1, 64 * nc, 64, 0, 128, blob + off, blob + off + 16384);
+    off += SLOT_BYTES;
+  }
+  for (int nc = 0; nc < 6; ++nc)    // layer 3: [64 rows x (128|128|64)]
+    for (int kc = 0; kc < 3; ++kc) {
+      const int kt = (kc < 2) ? 128 : 64;
+      const size_t hb = static_cast<size_t>(64) * kt * 2;
+      pack_tile(W3, K3, 64 * nc, 64, 128 * kc, kt, blob + off, blob + off + hb);
+      off += 2 * hb;
+    }
+  if (off != static_cast<size_t>(BLOB_BYTES)) SONET_FAIL(SONET_ERR_BAD_ARG, "pack: size mismatch");
+  float* f = fparams_host;
+  for (int c = 0; c < C0; ++c)
+    for (int i = 0; i < 6; ++i) f[c * 6 + i] = (i < Cin) ? W0[c * Cin + i] : 0.f;
+  std::memcpy(f + C0 * 6, shift0, C0 * 4);
+  std::memcpy(f + C0 * 6 + C0, shift1, C1 * 4);
+  std::memcpy(f + C0 * 6 + C0 + C1, shift2, C2 * 4);
+  std::memcpy(f + C0 * 6 + C0 + C1 + C2, shift3, C3 * 4);
+  return SONET_OK;
+}
+
+extern "C" int sonet_pointresnet_tc_forward(const float* x, int Cin, int B, int P, const void* blob,
+                                            const float* fparams, float* out,
+                                            sonet_stream_t stream) {
+  using namespace sonet;
+  using namespace sonet::pm;
+  SONET_REQUIRE(B >= 0 && P >= 0, "pointresnet_tc: negative dimension");
+  SONET_REQUIRE(Cin >= 1 && Cin <= 6, "pointresnet_tc: Cin=%d out of range [1,6]", Cin);
+  if (B == 0 || P == 0) return SONET_OK;
+  SONET_REQUIRE(x && blob && fparams && out, "pointresnet_tc: null pointer");
+  SONET_REQUIRE(aligned16(blob), "pointresnet_tc: weight blob must be 16-byte aligned");
+  const long long tiles = static_cast<long long>(B) * ((P + TILE - 1) / TILE);
+  SONET_REQUIRE(tiles < (1LL << 31), "pointresnet_tc: too many tiles");
+  SONET_REQUIRE(SMEM_BYTES <= max_smem_optin(), "pointresnet_tc: needs %d B of shared memory",
+                SMEM_BYTES);
+  cudaFuncSetAttribute(pointresnet_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       SMEM_BYTES);
+  const int grid = static_cast<int>(std::min<long long>(tiles, sm_count()));
+  pointresnet_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, as_stream(stream)>>>(
+      x, Cin, B, P, static_cast<const unsigned char*>(blob), fparams, out);
+  return check_launch("pointresnet_tc");
+}

@@ -1,0 +1,149 @@
+// tc_common.cuh — tcgen05 / TMEM / UMMA-descriptor helpers (sm_100a inline PTX).
+//
+// Encodings follow the PTX ISA "tcgen05" matrix/instruction descriptors (cross-checked against
+// the field layouts in CUTLASS cute/arch/mma_sm100_desc.hpp, which is only read, not included).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace sonet {
+namespace tc {
+
+// ---- TMEM allocation (one warp, .sync.aligned) -------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void fence_after_sync() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// all previously issued tcgen05.mma of this thread arrive on `bar` when complete
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+// ---- descriptors ---------------------------------------------------------------------------------
+// Instruction descriptor, kind::f16: D=F32 (c_format=1, bit 4), A=B=BF16 (format 1, bits 7 and
+// 10), both operands K-major (bits 15,16 = 0), N>>3 at bit 17, M>>4 at bit 24.
+__host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+// Shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleave"): the operand is stored as
+// core matrices of 8 rows x 16 bytes (128 contiguous bytes, row r at +16*r);
+//   LBO = byte distance between the two core matrices adjacent along K (bits 16..29, >>4)
+//   SBO = byte distance between 8-row groups along M/N            (bits 32..45, >>4)
+// bits 46..47 = descriptor version 1 (Blackwell); layout type (bits 61..63) = 0.
+__host__ __device__ constexpr uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) |
+         (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16) |
+         (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+// ---- MMA issue (single thread) -----------------------------------------------------------------
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                       uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]^T   (A: lane = row, 2 bf16 per 32-bit column along K)
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                       uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// ---- TMEM <-> registers: 32x32b shape = each thread its own lane, N consecutive 32-bit columns ----
+__device__ __forceinline__ void ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, "
+      "[%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
+// ---- bf16 hi/lo split of 16 fp32 values into 8 + 8 packed words -----------------------------------
+// word j of hi = {bf16(x[2j+1]) : bf16(x[2j])} (low half = even channel = lower K index);
+// lo = bf16(x - float(hi)). hi*W_hi + lo*W_hi + hi*W_lo reproduces the fp32 product to ~2^-16.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+__device__ __forceinline__ void split16(const float (&x)[16], uint32_t (&out)[16]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t h = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+    const float h0 = __uint_as_float(h << 16), h1 = __uint_as_float(h & 0xFFFF0000u);
+    out[j] = h;
+    out[8 + j] = pack_bf16x2(x[2 * j] - h0, x[2 * j + 1] - h1);
+  }
+}
+
+// bounded mbarrier wait: a protocol bug traps instead of hanging the GPU box
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity, int tag) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  printf("[sonet] mbarrier wait timed out: tag %d block %d thread %d parity %u\n", tag,
+         (int)blockIdx.x, (int)threadIdx.x, parity);
+  __trap();
+}
+
+}  // namespace tc
+}  // namespace sonet

@@ -41,6 +41,14 @@ _SIGNATURES = {
     "sonet_kcopy_mean_f32": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "sonet_chamfer_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sonet_pointresnet_tc_blob_bytes": [],
+    "sonet_pointresnet_tc_fparam_count": [],
+    "sonet_pointresnet_tc_pack": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p],
+    "sonet_pointresnet_tc_forward": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_void_p],
+    "sonet_debug_tc_probe": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                             c_void_p],
     "sonet_last_error_string": [],
     "sonet_version": [],
 }

@@ -255,3 +255,37 @@ def chamfer(pred, gt, want_idx=False):
               _stream(pred))
     return dict(loss=loss, fwd_arr=fa, bwd_arr=ba, elem_fwd=ef, elem_bwd=eb, idx_fwd=idx_f,
                 idx_bwd=idx_b)
+
+
+def pointresnet_tc_pack(W, shifts, cin):
+    """Host-side packing for pointresnet_tc: W = [W0 [64,cin], W1 [128,64], W2 [256,128],
+    W3 [384,320]] folded fp32 weights, shifts = 4 folded shift vectors (any device).
+    Returns (blob uint8 [bytes], fparams f32) as CPU tensors."""
+    lib = _C.lib()
+    Wc = [w.detach().to("cpu", torch.float32).contiguous() for w in W]
+    Sc = [s.detach().to("cpu", torch.float32).contiguous() for s in shifts]
+    want = [(64, cin), (128, 64), (256, 128), (384, 320)]
+    for w, sh, s in zip(Wc, want, Sc):
+        if tuple(w.shape) != sh or s.numel() != sh[0]:
+            raise RuntimeError("pointresnet_tc_pack: unexpected layer shape %s" % (tuple(w.shape),))
+    blob = torch.zeros(lib.sonet_pointresnet_tc_blob_bytes(), dtype=torch.uint8)
+    fparams = torch.zeros(lib.sonet_pointresnet_tc_fparam_count(), dtype=torch.float32)
+    _C.check(lib.sonet_pointresnet_tc_pack(Wc[0].data_ptr(), int(cin), Wc[1].data_ptr(),
+                                           Wc[2].data_ptr(), Wc[3].data_ptr(), Sc[0].data_ptr(),
+                                           Sc[1].data_ptr(), Sc[2].data_ptr(), Sc[3].data_ptr(),
+                                           blob.data_ptr(), fparams.data_ptr()),
+             "sonet_pointresnet_tc_pack")
+    return blob, fparams
+
+
+def pointresnet_tc(x, blob, fparams):
+    """x [B,Cin<=6,P] f32 -> [B,384,P]: the fused tcgen05 first PointResNet."""
+    _chk(x, "x", torch.float32)
+    _chk(blob, "blob", torch.uint8)
+    _chk(fparams, "fparams", torch.float32)
+    B, Cin, P = x.shape
+    with torch.cuda.device(x.device):
+        out = torch.empty((B, 384, P), dtype=torch.float32, device=x.device)
+        _call("sonet_pointresnet_tc_forward", _C.ptr(x), Cin, B, P, _C.ptr(blob), _C.ptr(fparams),
+              _C.ptr(out), _stream(x))
+    return out

@@ -64,3 +64,26 @@ def golden_case(g, task, **over):
     inp = synth.synth_inputs(B, N, opt.node_num, max(som_k, 1), seed=seed,
                              node_mode=str(g["node_mode"]))
     return opt, inp, seed
+
+
+def to_ref_slot_order(t, our_min_idx, g, k):
+    return to_slot_order(t, our_min_idx, torch.from_numpy(g["min_idx_ref"].astype(np.int64)), k)
+
+
+def to_slot_order(t, our_min_idx, ref, k):
+    """Reorder the k stacked copies of a [B,C,kN] tensor from OUR slot order (ascending distance)
+    to the slot order the reference run used (its topk(sorted=False) order is implementation
+    defined; parity for the assignment is per-point set equality — SURVEY.md Appendix C)."""
+    ref = ref.detach().cpu().long()                                     # [B,kN]
+    ours = our_min_idx.detach().cpu().long()
+    B, kN = ours.shape
+    N = kN // k
+    ours_k = ours.view(B, k, N)
+    ref_k = ref.view(B, k, N)
+    # src_slot[b, s, n] = our slot holding the node the reference has in slot s
+    match = ref_k.unsqueeze(2) == ours_k.unsqueeze(1)                   # [B, k_ref, k_ours, N]
+    assert bool(match.any(dim=2).all()), "assignment sets differ"
+    src_slot = match.float().argmax(dim=2)                              # [B,k,N]
+    src = (src_slot * N + torch.arange(N).view(1, 1, N)).view(B, kN)
+    tc = t.detach().cpu()
+    return torch.gather(tc, 2, src.unsqueeze(1).expand(B, tc.shape[1], kN))

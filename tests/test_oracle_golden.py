@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import assert_close, assert_golden, build_states, golden, golden_case
+from helpers import (assert_close, assert_golden, build_states, golden, golden_case,
+                     to_ref_slot_order)
 
 
 def test_index_max_oracle_vs_reference_binary(oracle_mod):
@@ -42,8 +43,12 @@ def test_classifier_oracle_vs_reference(oracle_mod, name):
     assert np.array_equal(o["mask_row_sum"].numpy(), g["mask_row_sum"])
     if "emptynodes" in name:
         assert (g["mask_row_max"] == 0).any(), "fixture must exercise empty nodes"
-    for n in ("som_node", "first_pn_out", "first_pn_out_masked_max", "final_pn_out", "feature"):
+    for n in ("som_node", "first_pn_out_masked_max", "final_pn_out", "feature"):
         assert_golden(g, n, o[n], tol=1e-5)
+    # per-copy tensors: compare in the slot order of the reference run (torch.topk(sorted=False)
+    # order may differ between machines)
+    assert_golden(g, "first_pn_out", to_ref_slot_order(o["first_pn_out"], o["min_idx"], g, opt.k),
+                  tol=1e-5)
     score = oracle_mod.classifier_forward(st["head"], o["feature"])
     assert_golden(g, "score", score, tol=1e-5)
 
@@ -54,8 +59,9 @@ def test_segmenter_oracle_vs_reference(oracle_mod):
     st = build_states("segmenter", opt, seed)
     o = oracle_mod.encoder_forward(st["encoder"], opt, inp["pc"], inp["sn"], inp["node"],
                                    inp["node_knn_I"])
-    assert_golden(g, "centers", o["centers"], tol=1e-6)
-    assert_golden(g, "x_decentered", o["x_decentered"], tol=1e-6)
+    assert_golden(g, "centers", to_ref_slot_order(o["centers"], o["min_idx"], g, opt.k), tol=1e-6)
+    assert_golden(g, "x_decentered",
+                  to_ref_slot_order(o["x_decentered"], o["min_idx"], g, opt.k), tol=1e-6)
     s = oracle_mod.segmenter_forward(st["head"], opt, o, inp["pc"], inp["sn"], inp["label"])
     assert_golden(g, "score_segmenter", s, tol=1e-5)
 
