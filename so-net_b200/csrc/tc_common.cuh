@@ -4,6 +4,7 @@
 // the field layouts in CUTLASS cute/arch/mma_sm100_desc.hpp, which is only read, not included).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -122,6 +123,23 @@ __device__ __forceinline__ void split16(const float (&x)[16], uint32_t (&out)[16
     const float h0 = __uint_as_float(h << 16), h1 = __uint_as_float(h & 0xFFFF0000u);
     out[j] = h;
     out[8 + j] = pack_bf16x2(x[2 * j] - h0, x[2 * j + 1] - h1);
+  }
+}
+
+// ---- fp16 hi/lo split (22 significant bits, vs 16 for bf16) ---------------------------------------
+// Same instruction kind (kind::f16) and rate as bf16; operands must stay inside the fp16 range
+// (|x| <= 65504) — callers clamp activations and pre-scale weights by a power of two.
+__host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+__device__ __forceinline__ void split16_f16(const float (&x)[16], uint32_t (&out)[16]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const __half2 h = __floats2half2_rn(x[2 * j], x[2 * j + 1]);  // .x (low half) = even channel
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x[2 * j] - hf.x, x[2 * j + 1] - hf.y);
+    out[j] = *reinterpret_cast<const uint32_t*>(&h);
+    out[8 + j] = *reinterpret_cast<const uint32_t*>(&l);
   }
 }
 
