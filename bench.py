@@ -39,6 +39,9 @@ UNIT = "clouds/s"
 B_PER_GPU, NPTS, M_NODES, SOM_K, K_NN, CLASSES = 64, 5000, 64, 9, 3, 40
 WORKLOAD = ("ModelNet40 classifier forward, batch=%d/GPU, N=%d pts, 8x8 SOM, k=%d, som_k=%d, "
             "fp32, eval (BASELINE.json configs[1])" % (B_PER_GPU, NPTS, K_NN, SOM_K))
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at this workload, from the committed
+# `ncu --set full` captures (profiles/r01_summary.md); None until a capture exists.
+NCU_TRAFFIC = {"index_max_f32": 1.4871e9}
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -71,7 +74,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -212,6 +215,15 @@ def kernel_report(profile_steps, peaks):
             row.update(bound="tensor", achieved=round(ach, 3), peak=tf, unit="TFLOP/s",
                        frac=round(ach / tf, 5), shape="[%d,%d+%d,%d]->%d" % (B, C0, C1, P, Cout),
                        note="fp32 CUDA-core path vs the bf16 tensor peak")
+        elif key.startswith("pointresnet_tc_forward"):
+            Bc, P = a[2], a[3]
+            flops = 328448.0 * Bc * P          # 2 * (6*64 + 64*128 + 128*256 + 320*384)
+            ach = flops / (ms * 1e-3) / 1e12
+            row.update(bound="tensor", achieved=round(ach, 2), peak=tf, unit="TFLOP/s",
+                       frac=round(ach / tf, 4), executed_tflops=round(3 * ach, 1),
+                       shape="[%d,%d,%d] 6->64->128->256->[320]->384" % (Bc, a[1], P),
+                       note="algorithmic flops; the fp16 hi/lo split executes 3x as many on "
+                            "the tensor pipe, so frac <= 0.33 by construction")
         elif key.startswith("index_max"):
             B, C, N, K = a[2], a[3], a[4], a[5]
             byts = 4.0 * B * C * N + 4.0 * B * N + 4.0 * B * C * K * (2 if a[7] else 1)
@@ -282,11 +294,14 @@ def main():
     # ---- (1) device-resident arm -------------------------------------------------------------------
     model.set_input(*host)
     torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index)
+    sampler.start()                                        # runs through both timed regions
     for _ in range(args.warmup):
         gpu_step()
-    sampler = ClockSampler(dev.index)
+    time.sleep(0.3)                                        # let nvidia-smi deliver its first sample
+    for _ in range(args.warmup):
+        gpu_step()
     barrier()
-    sampler.start()
     l0 = ops.KERNEL_LAUNCHES
     evs = []
     wall0 = time.perf_counter()
@@ -342,21 +357,17 @@ def main():
         ops.PROFILE = None
     kernels = kernel_report(prof_steps, peaks)
     kernel_ms = sum(r["ms"] for r in kernels)
-    dom = max(kernels, key=lambda r: r["ms"])
-    # the dominant op family: the point-wise layers of the first PointResNet
-    pw = [r for r in kernels if r["kernel"].startswith("pointwise_layer")]
-    pw_ms = sum(r["ms"] for r in pw)
-    pw_flops = 0.0
-    for r in pw:
-        pw_flops += r["achieved"] * 1e12 * r["ms"] * 1e-3
-    tf_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-    roofline = {"kernel": "pointwise_kernel (all %d 1x1-conv layers of the step)" % len(pw),
-                "bound": "tensor", "achieved": round(pw_flops / (pw_ms * 1e-3) / 1e12, 3),
-                "peak": tf_peak, "unit": "TFLOP/s",
-                "frac": round(pw_flops / (pw_ms * 1e-3) / 1e12 / tf_peak, 5),
-                "traffic": None, "peak_source": peaks["_source"] + " bf16 sustained",
-                "share_of_step": round(pw_ms / kernel_ms, 4),
-                "dominant_single_launch": dom["kernel"]}
+    # the dominant kernel = the launch with the largest measured device time among those with a
+    # roofline model (the fused tcgen05 PointResNet on the default path)
+    modelled = [r for r in kernels if "bound" in r]
+    dom = max(modelled, key=lambda r: r["ms"])
+    roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"],
+                "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"],
+                "traffic": NCU_TRAFFIC.get(dom["kernel"].split("#")[0]),
+                "peak_source": peaks["_source"] + (" bf16 sustained" if dom["bound"] == "tensor"
+                                                   else " copy bandwidth"),
+                "ms": dom["ms"], "share_of_step": round(dom["ms"] / kernel_ms, 4),
+                "note": dom.get("note")}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -180,6 +180,22 @@ int sonet_pointresnet_tc_pack(const float* W0, int Cin, const float* W1, const f
 int sonet_pointresnet_tc_forward(const float* x, int Cin, int B, int P, const void* blob,
                                  const float* fparams, float* out, sonet_stream_t stream);
 
+/* ---- a-8/a-9/a-10 on tensor cores: generic point-wise layer on tcgen05 --------------------------
+ * Same contract as sonet_pointwise_layer_f32 (EquivariantLayer / MyConv2d 1x1 eval forward,
+ * models/layers.py:203-210, 282-296) for layers dense enough for tensor cores (KNNModule,
+ * final PointNet, segmenter head). fp32 parity through the fp16 hi/lo 3-product split.
+ *   blob_bytes(Cout, Cin): size of the packed weight images.
+ *   pack (host pointers): W [Cout,Cin] row-major fp32 with the BN scale folded in -> blob_host,
+ *     *inv_scale = 1 / (power-of-two pre-scale applied to the weights).
+ *   forward (device pointers): as sonet_pointwise_layer_f32 with (blob, inv_scale) instead of
+ *     (Wt, scale). */
+long long sonet_pointwise_tc_blob_bytes(int Cout, int Cin);
+int sonet_pointwise_tc_pack(const float* W, int Cout, int Cin, void* blob_host, float* inv_scale);
+int sonet_pointwise_tc_forward(const float* x0, int C0, const float* x1, int C1, int B, int P,
+                               const void* blob, float inv_scale, const float* shift, int Cout,
+                               int relu, const float* addend, const int32_t* gidx, int G,
+                               float* out, sonet_stream_t stream);
+
 /* ---- diagnostics -------------------------------------------------------------------------------
  * One 128 x N x K bf16 GEMM on tcgen05 (fp32 accumulate in TMEM), D = bf16(A) * bf16(Bm)^T.
  * A [128,K], Bm [N,K], D [128,N] fp32 row-major device pointers. mode 0: A from shared memory

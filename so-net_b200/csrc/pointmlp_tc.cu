@@ -31,6 +31,7 @@
 //     lane = point) overlaps the MMAs of the next chunk.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -63,6 +64,10 @@ __host__ __device__ constexpr int stage_kt(int s) { return (s < 4 || ((s - 4) % 
 __host__ __device__ constexpr int stage_bytes(int s) { return stage_kt(s) * 64 * 2 * 2; }
 }  // namespace pm
 
+// CL = thread-block-cluster size: the CL CTAs of a cluster consume the same weight stream, each
+// fetches 1/CL of every stage from L2 and MULTICASTS it into all CL shared memories — the stream
+// (608 KB per 128-point tile) is what bounds this kernel, and this divides its L2 traffic by CL.
+template <int CL>
 __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
     pointresnet_tc_kernel(const float* __restrict__ x_in, int Cin, int B, int P,
                           const unsigned char* __restrict__ blob, const float* __restrict__ fparams,
@@ -86,15 +91,17 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_cloud = (P + TILE - 1) / TILE;
   const int num_tiles = B * tiles_per_cloud;
-  const int my_tiles = (static_cast<int>(blockIdx.x) < num_tiles)
-                           ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x
-                           : 0;
+  // every CTA runs the same number of iterations (a cluster consumes the weight stream in
+  // lockstep); iterations past the last tile compute on zeros and store nothing
+  const int my_tiles = (num_tiles + gridDim.x - 1) / gridDim.x;
+  constexpr uint16_t CL_MASK = static_cast<uint16_t>((1u << CL) - 1);
+  const uint32_t cta_rank = (CL > 1) ? tc::cluster_ctarank() : 0;
 
   for (int i = threadIdx.x; i < NFP; i += NUM_THREADS) fp[i] = fparams[i];
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CL);
     }
     mbar_init(b_act0, 8);
     mbar_init(b_d1, 1);
@@ -114,6 +121,7 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (CL > 1) tc::cluster_sync_all();   // peers' barriers are initialised before any multicast lands
   tc::fence_after_sync();
   const uint32_t tm = *tmem_ptr;
 
@@ -129,8 +137,14 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
           const uint32_t slot = q % NSLOT, use = q / NSLOT;
           if (use > 0) tc::mbar_wait_bounded(&empty[slot], (use - 1) & 1, 100 + s);
           const uint32_t bytes = stage_bytes(s);
-          mbar_arrive_expect_tx(&full[slot], bytes);
-          bulk_g2s(smem + OFF_RING + slot * SLOT_BYTES, blob + off, bytes, &full[slot]);
+          mbar_arrive_expect_tx(&full[slot], bytes);   // all CL slices land on this barrier
+          if (CL == 1) {
+            bulk_g2s(smem + OFF_RING + slot * SLOT_BYTES, blob + off, bytes, &full[slot]);
+          } else {
+            const uint32_t slice = bytes / CL;
+            tc::bulk_g2s_multicast(smem + OFF_RING + slot * SLOT_BYTES + cta_rank * slice,
+                                   blob + off + cta_rank * slice, slice, &full[slot], CL_MASK);
+          }
           off += bytes;
         }
       }
@@ -184,7 +198,7 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
             tc::mma_ts(d, a_lo, dh, IDESC, 1);
             tc::mma_ts(d, a_hi, dl, IDESC, 1);
           }
-          tc::commit(&empty[slot]);
+          if (CL == 1) tc::commit(&empty[slot]); else tc::commit_multicast(&empty[slot], CL_MASK);
         }
         tc::commit(b_d2);
         // ---- layer 3: D3[128 x 384] = cat(act0, act2)[128 x 320] * W3^T, six 64-column chunks ----
@@ -217,7 +231,7 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
               tc::mma_ts(d, a_lo, dh, IDESC, 1);
               tc::mma_ts(d, a_hi, dl, IDESC, 1);
             }
-            tc::commit(&empty[slot]);
+            if (CL == 1) tc::commit(&empty[slot]); else tc::commit_multicast(&empty[slot], CL_MASK);
           }
           tc::commit(&d3full[buf]);
         }
@@ -239,7 +253,7 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
       const int tile = blockIdx.x + t * gridDim.x;
       const int b = tile / tiles_per_cloud;
       const int j = (tile - b * tiles_per_cloud) * TILE + r;
-      const bool valid = j < P;
+      const bool valid = (tile < num_tiles) && (j < P);
       const uint32_t par = t & 1;
 
       // ---- layer 0 on CUDA cores: 32 of the 64 channels per warpgroup ----
@@ -338,6 +352,7 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (CL > 1) tc::cluster_sync_all();   // no CTA leaves while peers may still signal its barriers
   if (warp == 2) tc::tmem_dealloc(tm, 512);
 }
 
@@ -430,10 +445,33 @@ extern "C" int sonet_pointresnet_tc_forward(const float* x, int Cin, int B, int 
   SONET_REQUIRE(tiles < (1LL << 31), "pointresnet_tc: too many tiles");
   SONET_REQUIRE(SMEM_BYTES <= max_smem_optin(), "pointresnet_tc: needs %d B of shared memory",
                 SMEM_BYTES);
-  cudaFuncSetAttribute(pointresnet_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       SMEM_BYTES);
-  const int grid = static_cast<int>(std::min<long long>(tiles, sm_count()));
-  pointresnet_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, as_stream(stream)>>>(
-      x, Cin, B, P, static_cast<const unsigned char*>(blob), fparams, out);
+  // cluster size: 2 by default (148 SMs = 74 pairs, no stranded SMs); SONET_TC_CLUSTER=1|2|4
+  static int cl_env = -1;
+  if (cl_env < 0) {
+    const char* e = getenv("SONET_TC_CLUSTER");
+    cl_env = e ? atoi(e) : 2;
+    if (cl_env != 1 && cl_env != 2 && cl_env != 4) cl_env = 2;
+  }
+  int cl = cl_env;
+  const int sms = sm_count();
+  while (cl > 1 && (tiles < cl || sms % cl != 0)) cl >>= 1;
+  int grid = static_cast<int>(std::min<long long>(tiles, sms));
+  grid -= grid % cl;
+  auto kern = cl == 4 ? pointresnet_tc_kernel<4>
+                      : (cl == 2 ? pointresnet_tc_kernel<2> : pointresnet_tc_kernel<1>);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, x, Cin, B, P, static_cast<const unsigned char*>(blob), fparams, out);
   return check_launch("pointresnet_tc");
 }

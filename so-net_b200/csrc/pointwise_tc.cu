@@ -1,0 +1,338 @@
+// pointwise_tc.cu — generic point-wise shared-MLP layer (1x1 conv + folded BN + ReLU) on tcgen05.
+//
+// Same contract as sonet_pointwise_layer_f32 (csrc/pointwise.cu; EquivariantLayer / MyConv2d 1x1 eval
+// forward, models/layers.py:203-210, 282-296) for the layers that are dense enough for tensor
+// cores: KNNModule's 387->512->512 (models/layers.py:362-364), the final PointNet 515->768->1024
+// (models/networks.py:192) and the segmenter head (models/networks.py:326-341).
+//
+//   out[b,co,p] = act( inv * sum_ci Ws[co,ci] * X[b,ci,p] + shift[co] (+ addend[b,co,g(b,p)]) )
+//
+// Rows (b,p) are flattened and tiled by 128 = MMA M = TMEM lanes; an item is (row tile, 256-wide
+// out-channel tile); K streams in 64-channel chunks through a 2-stage ring:
+//   * converter warps (8): read the fp32 activations coalesced along p (thread = row), clamp to the
+//     fp16 range, split into fp16 hi/lo and write the K-major no-swizzle A images with one 128-bit
+//     shared store per 8 channels (conflict free), fence.proxy.async, arrive;
+//   * TMA warp: streams the pre-packed fp16 hi/lo weight images (cp.async.bulk + mbarrier);
+//   * MMA warp (one thread): 3 tcgen05.mma.kind::f16 per 16-channel K step (hi*hi + lo*hi + hi*lo),
+//     SS mode, M=128, N<=256, fp32 accumulation in TMEM, two 256-column accumulator buffers so the
+//     epilogue of item i overlaps the MMAs of item i+1;
+//   * epilogue warps (4): tcgen05.ld, fused scale/shift (+ gathered addend) + ReLU, stores with
+//     lane = row => 128-byte coalesced along p.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "tc_common.cuh"
+
+namespace sonet {
+namespace pwt {
+constexpr int TILE = 128, KCH = 64, NT = 256;
+constexpr int A_BYTES = 2 * TILE * KCH * 2;   // hi + lo images of the activation chunk, 32 KB
+constexpr int W_BYTES = 2 * NT * KCH * 2;     // hi + lo images of the weight chunk, 64 KB
+constexpr int NSTAGE = 2;
+constexpr int NUM_THREADS = 512;
+constexpr int OFF_A = 0;
+constexpr int OFF_W = OFF_A + NSTAGE * A_BYTES;
+constexpr int OFF_BAR = OFF_W + NSTAGE * W_BYTES;
+constexpr int NBAR = 3 * NSTAGE + 4;
+constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16;
+
+struct Dims {
+  int C0, C1, B, P, Cout, relu, G;
+  int kchunks;   // ceil(pad16(Cin) / 64)
+  int ntiles;    // out-channel tiles of <= 256 (each a multiple of 64)
+  int cin_pad;   // Cin rounded up to 16
+  float inv;     // 1 / weight pre-scale
+};
+__host__ __device__ inline int ntile_width(int Cout, int nt) {
+  const int cpad = (Cout + 63) / 64 * 64;
+  return min(NT, cpad - nt * NT);
+}
+}  // namespace pwt
+
+__global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
+    pointwise_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
+                        const unsigned char* __restrict__ blob, const float* __restrict__ shift,
+                        const float* __restrict__ addend, const int32_t* __restrict__ gidx,
+                        float* __restrict__ out, pwt::Dims d) {
+  using namespace pwt;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* full_w = bars;                  // [NSTAGE] TMA -> MMA
+  uint64_t* full_a = bars + NSTAGE;         // [NSTAGE] converters -> MMA
+  uint64_t* empty = bars + 2 * NSTAGE;      // [NSTAGE] MMA -> TMA + converters
+  uint64_t* d_full = bars + 3 * NSTAGE;     // [2] MMA -> epilogue
+  uint64_t* d_empty = d_full + 2;           // [2] epilogue -> MMA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long rows = static_cast<long long>(d.B) * d.P;
+  const int row_tiles = static_cast<int>((rows + TILE - 1) / TILE);
+  const int items = row_tiles * d.ntiles;   // n-tile fastest: the activation tile stays hot in L2
+  const int my_items =
+      (static_cast<int>(blockIdx.x) < items) ? (items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int Cin = d.C0 + d.C1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full_w[s], 1);
+      mbar_init(&full_a[s], 8);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&d_full[i], 1);
+      mbar_init(&d_empty[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tc::tmem_alloc(tmem_ptr, 512);
+    tc::tmem_relinquish();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tm = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producer: weight chunk images =================
+    if (lane == 0) {
+      uint32_t q = 0;
+      for (int it = 0; it < my_items; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int nt = item % d.ntiles;
+        const int nw = ntile_width(d.Cout, nt);
+        // blob offset of n-tile nt: all previous tiles are NT wide
+        size_t off = static_cast<size_t>(nt) * d.kchunks * W_BYTES;
+        const uint32_t bytes = static_cast<uint32_t>(nw) * KCH * 4;
+        for (int kc = 0; kc < d.kchunks; ++kc, ++q) {
+          const uint32_t slot = q % NSTAGE, use = q / NSTAGE;
+          if (use > 0) tc::mbar_wait_bounded(&empty[slot], (use - 1) & 1, 200);
+          mbar_arrive_expect_tx(&full_w[slot], bytes);
+          bulk_g2s(smem + OFF_W + slot * W_BYTES, blob + off, bytes, &full_w[slot]);
+          off += bytes;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t a_base = smem_u32(smem + OFF_A), w_base = smem_u32(smem + OFF_W);
+      uint32_t q = 0;
+      for (int it = 0; it < my_items; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int nt = item % d.ntiles;
+        const int nw = ntile_width(d.Cout, nt);
+        const uint32_t idesc = tc::idesc_f16_f32(TILE, nw);
+        const int buf = it & 1;
+        const uint32_t use = it >> 1;
+        if (use > 0) tc::mbar_wait_bounded(&d_empty[buf], (use - 1) & 1, 201);
+        tc::fence_after_sync();
+        const uint32_t dcol = tm + buf * NT;
+        for (int kc = 0; kc < d.kchunks; ++kc, ++q) {
+          const uint32_t slot = q % NSTAGE, par = (q / NSTAGE) & 1;
+          tc::mbar_wait_bounded(&full_w[slot], par, 202);
+          tc::mbar_wait_bounded(&full_a[slot], par, 203);
+          tc::fence_after_sync();
+          const uint32_t as = a_base + slot * A_BYTES, ws = w_base + slot * W_BYTES;
+          const int nks = min(4, (d.cin_pad - kc * KCH) / 16);
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint64_t ah = tc::smem_desc(as + ks * 256, 128, 1024),
+                           al = tc::smem_desc(as + A_BYTES / 2 + ks * 256, 128, 1024),
+                           bh = tc::smem_desc(ws + ks * 256, 128, 1024),
+                           bl = tc::smem_desc(ws + nw * KCH * 2 + ks * 256, 128, 1024);
+            tc::mma_ss(dcol, ah, bh, idesc, (kc | ks) != 0);
+            tc::mma_ss(dcol, al, bh, idesc, 1);
+            tc::mma_ss(dcol, ah, bl, idesc, 1);
+          }
+          tc::commit(&empty[slot]);
+        }
+        tc::commit(&d_full[buf]);
+      }
+    }
+  } else if (warp >= 8) {
+    // ================= converters: fp32 activations -> fp16 hi/lo K-major A images =================
+    const int t = threadIdx.x - 256;
+    const int m = t & 127, half = t >> 7;   // row in tile; which 32 of the chunk's 64 channels
+    uint32_t q = 0;
+    for (int it = 0; it < my_items; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const long long R = static_cast<long long>(item / d.ntiles) * TILE + m;
+      const bool valid = R < rows;
+      const int b = valid ? static_cast<int>(R / d.P) : 0;
+      const int p = valid ? static_cast<int>(R - static_cast<long long>(b) * d.P) : 0;
+      const float* r0 = x0 + static_cast<size_t>(b) * d.C0 * d.P + p;
+      const float* r1 = d.C1 ? x1 + static_cast<size_t>(b) * d.C1 * d.P + p : nullptr;
+      for (int kc = 0; kc < d.kchunks; ++kc, ++q) {
+        const int c_base = kc * KCH + half * 32;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int ci = c_base + i;
+          float x = 0.f;
+          if (valid && ci < Cin)
+            x = (ci < d.C0) ? __ldg(r0 + static_cast<size_t>(ci) * d.P)
+                            : __ldg(r1 + static_cast<size_t>(ci - d.C0) * d.P);
+          v[i] = fminf(fmaxf(x, -65504.f), 65504.f);
+        }
+        const uint32_t slot = q % NSTAGE, use = q / NSTAGE;
+        if (use > 0) tc::mbar_wait_bounded(&empty[slot], (use - 1) & 1, 204);
+        unsigned char* a_hi = smem + OFF_A + slot * A_BYTES + (m >> 3) * 1024 + (m & 7) * 16;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a = v[o * 8 + 2 * j], c = v[o * 8 + 2 * j + 1];
+            const __half2 h = __floats2half2_rn(a, c);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(a - hf.x, c - hf.y);
+            hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+          }
+          const int oct = half * 4 + o;
+          *reinterpret_cast<uint4*>(a_hi + oct * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(a_hi + A_BYTES / 2 + oct * 128) =
+              make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_a[slot]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int q4 = warp & 3;
+    const int m = q4 * 32 + lane;
+    const uint32_t lane_base = tm + (static_cast<uint32_t>(q4 * 32) << 16);
+    for (int it = 0; it < my_items; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int nt = item % d.ntiles;
+      const int nw = ntile_width(d.Cout, nt);
+      const long long R = static_cast<long long>(item / d.ntiles) * TILE + m;
+      const bool valid = R < rows;
+      const int b = valid ? static_cast<int>(R / d.P) : 0;
+      const int p = valid ? static_cast<int>(R - static_cast<long long>(b) * d.P) : 0;
+      const int buf = it & 1;
+      tc::mbar_wait_bounded(&d_full[buf], (it >> 1) & 1, 205);
+      tc::fence_after_sync();
+      float* orow = out + static_cast<size_t>(b) * d.Cout * d.P + p;
+      const float* arow = nullptr;
+      if (addend != nullptr && valid) {
+        const int g = min(max(__ldg(gidx + R), 0), d.G - 1);
+        arow = addend + static_cast<size_t>(b) * d.Cout * d.G + g;
+      }
+      for (int c0 = 0; c0 < nw; c0 += 16) {
+        uint32_t v[16];
+        tc::ld16(lane_base + buf * NT + c0, v);
+        tc::wait_ld();
+        if (c0 + 16 >= nw) {   // all columns of this buffer are in registers: release it
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&d_empty[buf]);
+        }
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int co = nt * NT + c0 + i;
+            if (co < d.Cout) {
+              float y = fmaf(__uint_as_float(v[i]), d.inv, shift ? __ldg(shift + co) : 0.f);
+              if (arow) y += __ldg(arow + static_cast<size_t>(co) * d.G);
+              orow[static_cast<size_t>(co) * d.P] = d.relu ? fmaxf(y, 0.f) : y;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tm, 512);
+}
+
+}  // namespace sonet
+
+extern "C" long long sonet_pointwise_tc_blob_bytes(int Cout, int Cin) {
+  using namespace sonet::pwt;
+  if (Cout < 1 || Cin < 1) return -1;
+  const int cpad = (Cout + 63) / 64 * 64;
+  const int kch = ((Cin + 15) / 16 * 16 + KCH - 1) / KCH;
+  return static_cast<long long>(cpad) * kch * KCH * 4;
+}
+
+extern "C" int sonet_pointwise_tc_pack(const float* W, int Cout, int Cin, void* blob_host,
+                                       float* inv_scale) {
+  using namespace sonet;
+  using namespace sonet::pwt;
+  SONET_REQUIRE(W && blob_host && inv_scale && Cout >= 1 && Cin >= 1, "pointwise_tc_pack: bad args");
+  const long long bytes = sonet_pointwise_tc_blob_bytes(Cout, Cin);
+  unsigned char* blob = static_cast<unsigned char*>(blob_host);
+  std::memset(blob, 0, static_cast<size_t>(bytes));
+  float mx = 0.f;
+  for (size_t i = 0, n = static_cast<size_t>(Cout) * Cin; i < n; ++i) mx = std::max(mx, std::fabs(W[i]));
+  float scale = 1.f;
+  if (mx > 0.f && std::isfinite(mx)) {
+    int e;
+    std::frexp(mx, &e);
+    scale = std::ldexp(1.f, 9 - e);   // max|scale*W| in [256, 512)
+  }
+  *inv_scale = 1.f / scale;
+  const int cpad = (Cout + 63) / 64 * 64;
+  const int kch = ((Cin + 15) / 16 * 16 + KCH - 1) / KCH;
+  const int ntiles = (cpad + NT - 1) / NT;
+  size_t off = 0;
+  for (int nt = 0; nt < ntiles; ++nt) {
+    const int nw = std::min(NT, cpad - nt * NT);
+    for (int kc = 0; kc < kch; ++kc) {
+      unsigned char* hi = blob + off;
+      unsigned char* lo = hi + static_cast<size_t>(nw) * KCH * 2;
+      for (int r = 0; r < nw; ++r) {
+        const int co = nt * NT + r;
+        if (co >= Cout) continue;
+        for (int k = 0; k < KCH; ++k) {
+          const int ci = kc * KCH + k;
+          if (ci >= Cin) continue;
+          const float w = W[static_cast<size_t>(co) * Cin + ci] * scale;
+          const __half h = __float2half_rn(w);
+          const __half l = __float2half_rn(w - __half2float(h));
+          const uint32_t o = (r >> 3) * 1024 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2;
+          std::memcpy(hi + o, &h, 2);
+          std::memcpy(lo + o, &l, 2);
+        }
+      }
+      off += static_cast<size_t>(nw) * KCH * 4;
+    }
+  }
+  return SONET_OK;
+}
+
+extern "C" int sonet_pointwise_tc_forward(const float* x0, int C0, const float* x1, int C1, int B,
+                                          int P, const void* blob, float inv_scale,
+                                          const float* shift, int Cout, int relu,
+                                          const float* addend, const int32_t* gidx, int G,
+                                          float* out, sonet_stream_t stream) {
+  using namespace sonet;
+  using namespace sonet::pwt;
+  SONET_REQUIRE(B >= 0 && P >= 0 && C0 >= 1 && C1 >= 0 && Cout >= 1, "pointwise_tc: bad dimension");
+  if (B == 0 || P == 0) return SONET_OK;
+  SONET_REQUIRE(x0 && blob && out, "pointwise_tc: null pointer");
+  SONET_REQUIRE(C1 == 0 || x1 != nullptr, "pointwise_tc: x1 null with C1=%d", C1);
+  SONET_REQUIRE(!addend || (gidx && G >= 1), "pointwise_tc: addend needs gidx and G");
+  SONET_REQUIRE(aligned16(blob), "pointwise_tc: weight blob must be 16-byte aligned");
+  Dims d;
+  d.C0 = C0; d.C1 = C1; d.B = B; d.P = P; d.Cout = Cout; d.relu = relu; d.G = G;
+  d.cin_pad = (C0 + C1 + 15) / 16 * 16;
+  d.kchunks = (d.cin_pad + KCH - 1) / KCH;
+  d.ntiles = ((Cout + 63) / 64 * 64 + NT - 1) / NT;
+  d.inv = inv_scale;
+  const long long rows = static_cast<long long>(B) * P;
+  const long long items = (rows + TILE - 1) / TILE * d.ntiles;
+  SONET_REQUIRE(items < (1LL << 31), "pointwise_tc: too many tiles");
+  SONET_REQUIRE(SMEM_BYTES <= max_smem_optin(), "pointwise_tc: needs %d B of shared memory", SMEM_BYTES);
+  cudaFuncSetAttribute(pointwise_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  const int grid = static_cast<int>(std::min<long long>(items, sm_count()));
+  pointwise_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, as_stream(stream)>>>(
+      x0, x1, static_cast<const unsigned char*>(blob), shift, addend, gidx, out, d);
+  return check_launch("pointwise_tc");
+}

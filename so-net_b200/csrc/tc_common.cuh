@@ -44,6 +44,34 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
                : "memory");
 }
 
+// as commit(), but arrives on the barrier at the same offset in every CTA of cta_mask (cluster)
+__device__ __forceinline__ void commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+// 1-D bulk copy global -> the same shared-memory offset of every CTA in cta_mask; each destination
+// CTA's mbarrier (same offset) receives complete_tx for `bytes`.
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src_gmem,
+                                                   uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---- descriptors ---------------------------------------------------------------------------------
 // Instruction descriptor, kind::f16: D=F32 (c_format=1, bit 4), A=B=BF16 (format 1, bits 7 and
 // 10), both operands K-major (bits 15,16 = 0), N>>3 at bit 17, M>>4 at bit 24.

@@ -47,12 +47,18 @@ _SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p],
     "sonet_pointresnet_tc_forward": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                      c_void_p],
+    "sonet_pointwise_tc_blob_bytes": [c_int, c_int],
+    "sonet_pointwise_tc_pack": [c_void_p, c_int, c_int, c_void_p, c_void_p],
+    "sonet_pointwise_tc_forward": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
+                                   ctypes.c_float, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                   c_int, c_void_p, c_void_p],
     "sonet_debug_tc_probe": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                              c_void_p],
     "sonet_last_error_string": [],
     "sonet_version": [],
 }
-_RESTYPE = {"sonet_last_error_string": ctypes.c_char_p, "sonet_version": ctypes.c_char_p}
+_RESTYPE = {"sonet_last_error_string": ctypes.c_char_p, "sonet_version": ctypes.c_char_p,
+            "sonet_pointwise_tc_blob_bytes": ctypes.c_longlong}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -176,10 +176,25 @@ class _PointwiseConvBase(nn.Module):
                 and self.normalization in (None, 'batch') and self.activation in (None, 'relu'))
 
     def forward_points(self, x0, x1=None, addend=None, gidx=None):
-        """x0 [B,C0,P] (+ x1 [B,C1,P] virtually concatenated on channels) -> [B,Cout,P]."""
-        w, shift = self._folded.get(self._conv_weight2d(), self.conv.bias,
-                                    self.norm if self.normalization == 'batch' else None,
-                                    transpose=True)
+        """x0 [B,C0,P] (+ x1 [B,C1,P] virtually concatenated on channels) -> [B,Cout,P].
+        Dense layers run on tcgen05 (csrc/pointwise_tc.cu, fp16 hi/lo split); thin ones on the
+        exact-fp32 CUDA-core kernel (csrc/pointwise.cu)."""
+        norm = self.norm if self.normalization == 'batch' else None
+        cin = x0.shape[1] + (0 if x1 is None else x1.shape[1])
+        cout = self.conv.out_channels
+        rows = x0.shape[0] * x0.shape[2]
+        if cin >= 32 and cout >= 64 and rows >= 1024 and os.environ.get("SONET_TC", "1") != "0":
+            w, shift = self._folded.get(self._conv_weight2d(), self.conv.bias, norm,
+                                        transpose=False)
+            key = (self._folded.version, w.data_ptr())
+            if getattr(self, "_tc_key", None) != key:
+                blob, inv = ops.pointwise_tc_pack(w)
+                self._tc_pack = (blob.to(w.device), inv)
+                self._tc_key = key
+            blob, inv = self._tc_pack
+            return ops.pointwise_layer_tc(x0, blob, inv, shift, cout, self.activation == 'relu',
+                                          x1=x1, addend=addend, gidx=gidx)
+        w, shift = self._folded.get(self._conv_weight2d(), self.conv.bias, norm, transpose=True)
         return ops.pointwise_layer(x0, w, None, shift, self.activation == 'relu', x1=x1,
                                    addend=addend, gidx=gidx)
 

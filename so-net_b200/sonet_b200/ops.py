@@ -289,3 +289,35 @@ def pointresnet_tc(x, blob, fparams):
         _call("sonet_pointresnet_tc_forward", _C.ptr(x), Cin, B, P, _C.ptr(blob), _C.ptr(fparams),
               _C.ptr(out), _stream(x))
     return out
+
+
+def pointwise_tc_pack(W):
+    """W [Cout,Cin] folded fp32 (any device) -> (blob uint8 CPU tensor, inv_scale float)."""
+    import ctypes
+    lib = _C.lib()
+    Wc = W.detach().to("cpu", torch.float32).contiguous()
+    Cout, Cin = Wc.shape
+    blob = torch.zeros(int(lib.sonet_pointwise_tc_blob_bytes(Cout, Cin)), dtype=torch.uint8)
+    inv = ctypes.c_float(0.0)
+    _C.check(lib.sonet_pointwise_tc_pack(Wc.data_ptr(), Cout, Cin, blob.data_ptr(),
+                                         ctypes.addressof(inv)), "sonet_pointwise_tc_pack")
+    return blob, float(inv.value)
+
+
+def pointwise_layer_tc(x0, blob, inv_scale, shift, cout, relu, x1=None, addend=None, gidx=None):
+    """tcgen05 variant of pointwise_layer: x0 [B,C0,P] (+ x1) -> [B,cout,P]."""
+    _chk(x0, "x0", torch.float32)
+    _chk(x1, "x1", torch.float32, optional=True)
+    _chk(blob, "blob", torch.uint8)
+    _chk(shift, "shift", torch.float32, optional=True)
+    _chk(addend, "addend", torch.float32, optional=True)
+    _chk(gidx, "gidx", torch.int32, optional=True)
+    B, C0, P = x0.shape
+    C1 = 0 if x1 is None else x1.shape[1]
+    G = 0 if addend is None else addend.shape[2]
+    with torch.cuda.device(x0.device):
+        out = torch.empty((B, cout, P), dtype=torch.float32, device=x0.device)
+        _call("sonet_pointwise_tc_forward", _C.ptr(x0), C0, _C.ptr(x1), C1, B, P, _C.ptr(blob),
+              float(inv_scale), _C.ptr(shift), int(cout), int(bool(relu)), _C.ptr(addend),
+              _C.ptr(gidx), G, _C.ptr(out), _stream(x0))
+    return out

@@ -99,3 +99,50 @@ def test_pointresnet_tc_repacks_after_weight_update(monkeypatch):
         net.layers[3].conv.bias.add_(1.0)
         b = net(x)
     assert torch.allclose(b, a + 1.0, atol=1e-5)
+
+
+# ---- the generic tcgen05 point-wise layer (csrc/pointwise_tc.cu) ------------------------------------
+@pytest.mark.parametrize("B,C0,C1,P,Cout,relu", [
+    (2, 387, 0, 576, 512, True),      # KNNModule layer 1 (K padded 387 -> 400)
+    (2, 512, 0, 576, 512, True),      # KNNModule layer 2
+    (16, 3, 512, 64, 768, True),      # final PointNet layer 1: two sources, 64 rows per cloud
+    (16, 768, 0, 64, 1024, False),    # final PointNet layer 2 (bare), 4 out-channel tiles
+    (1, 128, 0, 3072, 50, False),     # segmenter layer 5: Cout padded 50 -> 64
+    (3, 64, 0, 1000, 128, True),      # ragged row count
+    (2, 1024, 0, 1536, 512, True),    # segmenter layer 2
+])
+def test_pointwise_tc_vs_fp64(B, C0, C1, P, Cout, relu):
+    import torch.nn.functional as F
+    from helpers import assert_close
+    from sonet_b200 import ops
+    rs = np.random.RandomState(C0 + P + Cout)
+    x0 = torch.from_numpy(rs.normal(size=(B, C0, P)).astype(np.float32))
+    x1 = torch.from_numpy(rs.normal(size=(B, C1, P)).astype(np.float32)) if C1 else None
+    W = torch.from_numpy((rs.normal(size=(Cout, C0 + C1)) * np.sqrt(2.0 / (C0 + C1))).astype(np.float32))
+    shift = torch.from_numpy(rs.normal(size=Cout).astype(np.float32))
+    xin = x0 if x1 is None else torch.cat((x0, x1), 1)
+    want = F.conv1d(xin.double(), W.double().unsqueeze(2)) + shift.double()[None, :, None]
+    want = (F.relu(want) if relu else want).float()
+    blob, inv = ops.pointwise_tc_pack(W)
+    got = ops.pointwise_layer_tc(x0.to(DEV), blob.to(DEV), inv, shift.to(DEV), Cout, relu,
+                                 x1=None if x1 is None else x1.to(DEV))
+    assert got.shape == (B, Cout, P)
+    assert_close(got, want, "tcgen05 generic layer vs fp64", 2e-5)
+
+
+def test_pointwise_tc_gathered_addend():
+    import torch.nn.functional as F
+    from helpers import assert_close
+    from sonet_b200 import ops
+    rs = np.random.RandomState(0)
+    B, C0, P, Cout, G = 2, 396, 1536, 1024, 64
+    x0 = torch.from_numpy(rs.normal(size=(B, C0, P)).astype(np.float32))
+    W = torch.from_numpy((rs.normal(size=(Cout, C0)) / 20).astype(np.float32))
+    add = torch.from_numpy(rs.normal(size=(B, Cout, G)).astype(np.float32))
+    gidx = torch.from_numpy(rs.randint(0, G, size=(B, P)).astype(np.int32))
+    want = F.relu(F.conv1d(x0.double(), W.double().unsqueeze(2)) +
+                  torch.gather(add.double(), 2, gidx.long().unsqueeze(1).expand(B, Cout, P))).float()
+    blob, inv = ops.pointwise_tc_pack(W)
+    got = ops.pointwise_layer_tc(x0.to(DEV), blob.to(DEV), inv, None, Cout, True,
+                                 addend=add.to(DEV), gidx=gidx.to(DEV))
+    assert_close(got, want, "tcgen05 layer + gathered addend", 2e-5)
