@@ -202,6 +202,12 @@ int sonet_pointwise_tc_forward(const float* x0, int C0, const float* x1, int C1,
  * (SS), 1: A from tensor memory (TS). layout 0/1 selects which of the two canonical no-swizzle
  * K-major core-matrix arrangements is used; swap_fields exchanges the LBO/SBO descriptor fields.
  * Exists so that tests can pin the descriptor encodings the fused point-MLP kernel relies on. */
+/* Same as sonet_pointresnet_tc_forward, additionally writing clock64() stamps of the phase
+ * boundaries of CTA 0's 4th tile into timeline64[64] (device): [0..31] MMA warp, [32..63] an
+ * epilogue warp. Used by tools/tc_timeline.py to see where a tile's cycles go. */
+int sonet_debug_pointresnet_tc_timeline(const float* x, int Cin, int B, int P, const void* blob,
+                                        const float* fparams, float* out, long long* timeline64,
+                                        sonet_stream_t stream);
 int sonet_debug_tc_probe(const float* A, const float* Bm, int N, int K, int mode, int layout,
                          int swap_fields, float* D, sonet_stream_t stream);
 

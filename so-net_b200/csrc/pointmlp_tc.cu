@@ -21,19 +21,23 @@
 //     pre-scaled per layer by a power of two (undone exactly in the epilogue FMA) so their lo
 //     halves stay normal fp16 numbers; activations are clamped to the fp16 range (65504);
 //   * weights (B operand, K-major no-swizzle core-matrix images packed once by the host) stream
-//     L2 -> shared memory through a 5-slot TMA ring (cp.async.bulk + mbarrier), layer-1 weights stay
-//     resident; each 32 KB slot is a [64 out-channels x 128 in-channels] hi+lo tile;
-//   * warp roles: warp 0 TMA producer, warp 1 MMA issuer (one thread), warps 4-11 epilogue
-//     (two warpgroups splitting the columns; warp%4 selects the TMEM lane quarter);
-//   * TMEM map (512 columns): [0,64) act0 | [64,192) D1/act1, later two D3 buffers |
-//     [192,448) D2/act2 | [448,512) third D3 buffer. Layer 3 is issued as six 64-channel chunks
-//     rotating over the three D3 buffers so that its epilogue (shift add + coalesced fp32 stores,
-//     lane = point) overlaps the MMAs of the next chunk.
+//     L2 -> shared memory through a 5-slot TMA ring (cp.async.bulk + mbarrier); layer-1 weights
+//     stay resident;
+//   * MMA shapes are as wide as TMEM allows, because ONE thread issues them and the issue rate is
+//     what bounded the first version (480 N=64 MMAs per tile: measured 100 -> 60 cycles per MMA
+//     against 32 cycles of tensor work): layer 1 = 12 MMAs of N=128, layer 2 = 24 of N=256,
+//     layer 3 = 4 chunks x 60 of N=96 over two accumulator buffers (its epilogue — shift add +
+//     coalesced fp32 stores, lane = point — overlaps the next chunk's MMAs): 276 MMAs per tile;
+//   * the MMA warp stays converged and `elect.sync` predicates each tcgen05 instruction (issuing
+//     from a divergent `if (lane == 0)` makes nvcc wrap every UTCHMMA in an ELECT/BRA loop);
+//   * warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11
+//     epilogue (two warpgroups splitting the columns; warp%4 selects the TMEM lane quarter);
+//   * TMEM map (512 columns): [0,64) act0 | [64,320) D2/act2 | [320,448) D1/act1, and after
+//     layer 2: [320,416), [416,512) the two D3 buffers.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
-#include <vector>
 
 #include "tc_common.cuh"
 
@@ -44,11 +48,16 @@ constexpr int C0 = 64, C1 = 128, C2 = 256, C3 = 384, K3 = C0 + C2;  // layer wid
 constexpr int TILE = 128;                                            // points per tile (MMA M)
 constexpr int SLOT_BYTES = 32768, NSLOT = 5;
 constexpr int W1_BYTES = 2 * C1 * C0 * 2;                            // hi + lo images, 32 KB
-constexpr int STAGES_PER_TILE = 4 + 18;
-constexpr int BLOB_BYTES = W1_BYTES + 4 * SLOT_BYTES + 6 * (2 * SLOT_BYTES + SLOT_BYTES / 2);
-constexpr int NFP = C0 * 6 + C0 + C1 + C2 + C3 + 4;                  // W0 | shift0..3 | 1/wscale1..3
+constexpr int L2_STAGES = 4, L2_KT = 32;                             // [256 rows x 32 k] per stage
+constexpr int L3_CHUNKS = 4, L3_N = 96, L3_KSTAGES = 5, L3_KT = 64;  // [96 rows x 64 k] per stage
+constexpr int L2_STAGE_BYTES = C2 * L2_KT * 2 * 2;                   // 32768
+constexpr int L3_STAGE_BYTES = L3_N * L3_KT * 2 * 2;                 // 24576
+constexpr int STAGES_PER_TILE = L2_STAGES + L3_CHUNKS * L3_KSTAGES;  // 24
+constexpr int BLOB_BYTES =
+    W1_BYTES + L2_STAGES * L2_STAGE_BYTES + L3_CHUNKS * L3_KSTAGES * L3_STAGE_BYTES;  // 655360
+constexpr int NFP = C0 * 6 + C0 + C1 + C2 + C3 + 4;   // W0 | shift0..3 | 1/wscale1..3 (floats)
 constexpr int NUM_THREADS = 384;
-constexpr int NBAR = 2 * NSLOT + 5 + 6 + 1;
+constexpr int NBAR = 2 * NSLOT + 5 + 4 + 1;
 // shared memory carve-up
 constexpr int OFF_W1 = 0;
 constexpr int OFF_RING = OFF_W1 + W1_BYTES;
@@ -57,22 +66,36 @@ constexpr int OFF_BAR = OFF_FP + NFP * 4;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 // TMEM columns
-constexpr uint32_t COL_A0 = 0, COL_D1 = 64, COL_D2 = 192;
-__device__ __forceinline__ uint32_t d3_col(int buf) { return buf == 0 ? 448u : 64u * buf; }
+constexpr uint32_t COL_A0 = 0, COL_D2 = 64, COL_D1 = 320, COL_D3 = 320;
 
-__host__ __device__ constexpr int stage_kt(int s) { return (s < 4 || ((s - 4) % 3) < 2) ? 128 : 64; }
-__host__ __device__ constexpr int stage_bytes(int s) { return stage_kt(s) * 64 * 2 * 2; }
+__host__ __device__ constexpr int stage_bytes(int s) {
+  return s < L2_STAGES ? L2_STAGE_BYTES : L3_STAGE_BYTES;
+}
+// descriptor: lo word = start address >> 4 | (LBO=128 >> 4) << 16; hi word = SBO >> 4 | version 1.
+// Advancing the start address by n bytes is desc + (n >> 4).
+__device__ __forceinline__ uint64_t bdesc(uint32_t saddr, uint32_t sbo) {
+  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (8u << 16);
+  const uint32_t hi = (sbo >> 4) | (1u << 14);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
 }  // namespace pm
 
 // CL = thread-block-cluster size: the CL CTAs of a cluster consume the same weight stream, each
-// fetches 1/CL of every stage from L2 and MULTICASTS it into all CL shared memories — the stream
-// (608 KB per 128-point tile) is what bounds this kernel, and this divides its L2 traffic by CL.
+// fetches 1/CL of every stage from L2 and multicasts it into all CL shared memories. Measured: no
+// gain at CL=2 and a loss at CL=4 (the stream is not the bound; lockstep coupling costs), so the
+// default is CL=1; kept as a tested option (SONET_TC_CLUSTER).
 template <int CL>
 __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
     pointresnet_tc_kernel(const float* __restrict__ x_in, int Cin, int B, int P,
                           const unsigned char* __restrict__ blob, const float* __restrict__ fparams,
-                          float* __restrict__ out) {
+                          float* __restrict__ out, long long* __restrict__ dbg) {
   using namespace pm;
+  // optional timeline (debug entry point only): clock64 at phase boundaries of CTA 0's 4th tile
+#define PM_TL(role, idx)                                                          \
+  do {                                                                            \
+    if (dbg != nullptr && blockIdx.x == 0 && t == 3 && lane == 0)                 \
+      dbg[(role) * 32 + (idx)] = clock64();                                       \
+  } while (0)
   extern __shared__ __align__(1024) unsigned char smem[];
   float* fp = reinterpret_cast<float*>(smem + OFF_FP);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -83,9 +106,9 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
   uint64_t* b_act1 = b_act0 + 2;
   uint64_t* b_d2 = b_act0 + 3;
   uint64_t* b_act2 = b_act0 + 4;
-  uint64_t* d3full = b_act0 + 5;           // [3]
-  uint64_t* d3empty = d3full + 3;          // [3]
-  uint64_t* w1_full = d3empty + 3;
+  uint64_t* d3full = b_act0 + 5;           // [2]
+  uint64_t* d3empty = d3full + 2;          // [2]
+  uint64_t* w1_full = d3empty + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -108,7 +131,7 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
     mbar_init(b_act1, 8);
     mbar_init(b_d2, 1);
     mbar_init(b_act2, 8);
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&d3full[i], 1);
       mbar_init(&d3empty[i], 8);
     }
@@ -150,91 +173,93 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer (one thread) ===========================
-    if (lane == 0) {
-      constexpr uint32_t IDESC = tc::idesc_f16_f32(TILE, 64);
-      const uint32_t w1_addr = smem_u32(smem + OFF_W1);
-      const uint32_t ring_addr = smem_u32(smem + OFF_RING);
-      tc::mbar_wait_bounded(w1_full, 0, 1);
-      uint32_t q = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        const uint32_t par = t & 1;
-        // ---- layer 1: D1[128 x 128] = act0[128 x 64] * W1^T, two 64-column chunks ----
-        tc::mbar_wait_bounded(b_act0, par, 2);
-        if (t > 0) {  // D1 overlaps D3 buffers 1,2 of the previous tile: wait for their drain
-          tc::mbar_wait_bounded(&d3empty[1], 1, 3);
-          tc::mbar_wait_bounded(&d3empty[2], 1, 4);
-        }
-        tc::fence_after_sync();
+    // ============ MMA issuer: the warp stays converged, elect.sync issues from one lane ============
+    constexpr uint32_t ID1 = tc::idesc_f16_f32(TILE, C1), ID2 = tc::idesc_f16_f32(TILE, C2),
+                       ID3 = tc::idesc_f16_f32(TILE, L3_N);
+    const uint32_t w1_addr = smem_u32(smem + OFF_W1);
+    const uint32_t ring_addr = smem_u32(smem + OFF_RING);
+    tc::mbar_wait_bounded(w1_full, 0, 1);
+    uint32_t q = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const uint32_t par = t & 1;
+      // ---- layer 1: D1[128 x 128] = act0[128 x 64] * W1^T (one N=128 MMA per product) ----
+      tc::mbar_wait_bounded(b_act0, par, 2);
+      if (t > 0) {  // D1 overlaps both D3 buffers of the previous tile: wait for their last drain
+        tc::mbar_wait_bounded(&d3empty[0], 1, 3);
+        tc::mbar_wait_bounded(&d3empty[1], 1, 4);
+      }
+      tc::fence_after_sync();
+      PM_TL(0, 0);
+      {
+        const uint64_t dh0 = bdesc(w1_addr, 1024), dl0 = bdesc(w1_addr + W1_BYTES / 2, 1024);
 #pragma unroll
-        for (int nc = 0; nc < 2; ++nc) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t a_hi = tm + COL_A0 + 16 * ks, a_lo = a_hi + 8;
-            const uint32_t bh = w1_addr + nc * 8192 + ks * 256, bl = bh + 16384;
-            const uint64_t dh = tc::smem_desc(bh, 128, 1024), dl = tc::smem_desc(bl, 128, 1024);
-            const uint32_t d = tm + COL_D1 + 64 * nc;
-            tc::mma_ts(d, a_hi, dh, IDESC, ks > 0);
-            tc::mma_ts(d, a_lo, dh, IDESC, 1);
-            tc::mma_ts(d, a_hi, dl, IDESC, 1);
-          }
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t a_hi = tm + COL_A0 + 16 * ks, a_lo = a_hi + 8;
+          const uint64_t dh = dh0 + ks * 16, dl = dl0 + ks * 16;   // +256 B per K step
+          tc::mma_ts_elect(tm + COL_D1, a_hi, dh, ID1, ks > 0);
+          tc::mma_ts_elect(tm + COL_D1, a_lo, dh, ID1, 1);
+          tc::mma_ts_elect(tm + COL_D1, a_hi, dl, ID1, 1);
         }
-        tc::commit(b_d1);
-        // ---- layer 2: D2[128 x 256] = act1[128 x 128] * W2^T, four streamed 64-column chunks ----
-        tc::mbar_wait_bounded(b_act1, par, 5);
+      }
+      tc::commit_elect(b_d1);
+      PM_TL(0, 1);
+      // ---- layer 2: D2[128 x 256] = act1[128 x 128] * W2^T: 4 streamed K slabs of 32, N=256 ----
+      tc::mbar_wait_bounded(b_act1, par, 5);
+      tc::fence_after_sync();
+      PM_TL(0, 2);
+#pragma unroll
+      for (int kc = 0; kc < L2_STAGES; ++kc, ++q) {
+        const uint32_t slot = q % NSLOT;
+        tc::mbar_wait_bounded(&full[slot], (q / NSLOT) & 1, 6);
         tc::fence_after_sync();
-        for (int nc = 0; nc < 4; ++nc, ++q) {
+        const uint32_t sb = ring_addr + slot * SLOT_BYTES;
+        const uint64_t dh0 = bdesc(sb, 512), dl0 = bdesc(sb + L2_STAGE_BYTES / 2, 512);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint32_t a_hi = tm + COL_D1 + 16 * (kc * 2 + ks), a_lo = a_hi + 8;
+          const uint64_t dh = dh0 + ks * 16, dl = dl0 + ks * 16;
+          tc::mma_ts_elect(tm + COL_D2, a_hi, dh, ID2, (kc | ks) != 0);
+          tc::mma_ts_elect(tm + COL_D2, a_lo, dh, ID2, 1);
+          tc::mma_ts_elect(tm + COL_D2, a_hi, dl, ID2, 1);
+        }
+        if (CL == 1) tc::commit_elect(&empty[slot]);
+        else tc::commit_multicast_elect(&empty[slot], CL_MASK);
+      }
+      tc::commit_elect(b_d2);
+      PM_TL(0, 3);
+      // ---- layer 3: D3[128 x 384] = cat(act0, act2)[128 x 320] * W3^T: 4 chunks of N=96 ----
+      tc::mbar_wait_bounded(b_act2, par, 7);
+      tc::fence_after_sync();
+      PM_TL(0, 4);
+#pragma unroll 1
+      for (int nc = 0; nc < L3_CHUNKS; ++nc) {
+        const int buf = nc & 1;
+        if (nc >= 2) tc::mbar_wait_bounded(&d3empty[buf], 0, 8);   // drain of chunk nc-2 (this tile)
+        tc::fence_after_sync();
+        const uint32_t d = tm + COL_D3 + L3_N * buf;
+        PM_TL(0, 5 + 2 * nc);
+#pragma unroll
+        for (int kc = 0; kc < L3_KSTAGES; ++kc, ++q) {
           const uint32_t slot = q % NSLOT;
-          tc::mbar_wait_bounded(&full[slot], (q / NSLOT) & 1, 6);
+          tc::mbar_wait_bounded(&full[slot], (q / NSLOT) & 1, 10);
           tc::fence_after_sync();
           const uint32_t sb = ring_addr + slot * SLOT_BYTES;
+          const uint64_t dh0 = bdesc(sb, 1024), dl0 = bdesc(sb + L3_STAGE_BYTES / 2, 1024);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t a_hi = tm + COL_D1 + 16 * ks, a_lo = a_hi + 8;
-            const uint64_t dh = tc::smem_desc(sb + ks * 256, 128, 2048),
-                           dl = tc::smem_desc(sb + 16384 + ks * 256, 128, 2048);
-            const uint32_t d = tm + COL_D2 + 64 * nc;
-            tc::mma_ts(d, a_hi, dh, IDESC, ks > 0);
-            tc::mma_ts(d, a_lo, dh, IDESC, 1);
-            tc::mma_ts(d, a_hi, dl, IDESC, 1);
+          for (int ks = 0; ks < 4; ++ks) {
+            const int kg = kc * 4 + ks;  // 16-channel K group: 0-3 act0, 4-19 act2
+            const uint32_t a_hi = tm + (kg < 4 ? COL_A0 + 16 * kg : COL_D2 + 16 * (kg - 4));
+            const uint32_t a_lo = a_hi + 8;
+            const uint64_t dh = dh0 + ks * 16, dl = dl0 + ks * 16;
+            tc::mma_ts_elect(d, a_hi, dh, ID3, kg > 0);
+            tc::mma_ts_elect(d, a_lo, dh, ID3, 1);
+            tc::mma_ts_elect(d, a_hi, dl, ID3, 1);
           }
-          if (CL == 1) tc::commit(&empty[slot]); else tc::commit_multicast(&empty[slot], CL_MASK);
+          if (CL == 1) tc::commit_elect(&empty[slot]);
+          else tc::commit_multicast_elect(&empty[slot], CL_MASK);
         }
-        tc::commit(b_d2);
-        // ---- layer 3: D3[128 x 384] = cat(act0, act2)[128 x 320] * W3^T, six 64-column chunks ----
-        tc::mbar_wait_bounded(b_act2, par, 7);
-        tc::fence_after_sync();
-        for (int nc = 0; nc < 6; ++nc) {
-          const int buf = nc % 3;
-          if (nc >= 3) {
-            tc::mbar_wait_bounded(&d3empty[buf], 0, 8);   // drain of chunk nc-3 (this tile)
-          } else if (nc == 0 && t > 0) {
-            tc::mbar_wait_bounded(&d3empty[0], 1, 9);     // drain of chunk 3 of the previous tile
-          }
-          tc::fence_after_sync();
-          const uint32_t d = tm + d3_col(buf);
-          for (int kc = 0; kc < 3; ++kc, ++q) {
-            const uint32_t slot = q % NSLOT;
-            tc::mbar_wait_bounded(&full[slot], (q / NSLOT) & 1, 10);
-            tc::fence_after_sync();
-            const uint32_t sb = ring_addr + slot * SLOT_BYTES;
-            const int nks = (kc < 2) ? 8 : 4;
-            const uint32_t hi_bytes = (kc < 2) ? 16384u : 8192u;
-            const uint32_t sbo = (kc < 2) ? 2048u : 1024u;
-            for (int ks = 0; ks < nks; ++ks) {
-              const int kg = kc * 8 + ks;  // global 16-channel K group: 0-3 act0, 4-19 act2
-              const uint32_t a_hi = tm + (kg < 4 ? COL_A0 + 16 * kg : COL_D2 + 16 * (kg - 4));
-              const uint32_t a_lo = a_hi + 8;
-              const uint64_t dh = tc::smem_desc(sb + ks * 256, 128, sbo),
-                             dl = tc::smem_desc(sb + hi_bytes + ks * 256, 128, sbo);
-              tc::mma_ts(d, a_hi, dh, IDESC, kg > 0);
-              tc::mma_ts(d, a_lo, dh, IDESC, 1);
-              tc::mma_ts(d, a_hi, dl, IDESC, 1);
-            }
-            if (CL == 1) tc::commit(&empty[slot]); else tc::commit_multicast(&empty[slot], CL_MASK);
-          }
-          tc::commit(&d3full[buf]);
-        }
+        tc::commit_elect(&d3full[buf]);
+        PM_TL(0, 6 + 2 * nc);
       }
     }
   } else if (warp >= 4) {
@@ -257,6 +282,7 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
       const uint32_t par = t & 1;
 
       // ---- layer 0 on CUDA cores: 32 of the 64 channels per warpgroup ----
+      if (warp == 4) PM_TL(1, 0);
       float x[6];
 #pragma unroll
       for (int c = 0; c < 6; ++c)
@@ -281,10 +307,12 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(b_act0);
+      if (warp == 4) PM_TL(1, 1);
 
       // ---- layer 1 epilogue: 64 of 128 channels, in place ----
       tc::mbar_wait_bounded(b_d1, par, 20);
       tc::fence_after_sync();
+      if (warp == 4) PM_TL(1, 2);
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int ch0 = 64 * h + 16 * g;
@@ -302,10 +330,12 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(b_act1);
+      if (warp == 4) PM_TL(1, 3);
 
       // ---- layer 2 epilogue: 128 of 256 channels, in place ----
       tc::mbar_wait_bounded(b_d2, par, 21);
       tc::fence_after_sync();
+      if (warp == 4) PM_TL(1, 4);
 #pragma unroll 2
       for (int g = 0; g < 8; ++g) {
         const int ch0 = 128 * h + 16 * g;
@@ -323,22 +353,26 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(b_act2);
+      if (warp == 4) PM_TL(1, 5);
 
-      // ---- layer 3 epilogue: six chunks, 32 of each chunk's 64 channels; bare layer (no ReLU) ----
+      // ---- layer 3 epilogue: four chunks of 96 channels, 48 per warpgroup; bare layer (no ReLU) ----
       float* orow = out + (static_cast<size_t>(b) * C3) * P + j;
-      for (int nc = 0; nc < 6; ++nc) {
-        const int buf = nc % 3;
-        tc::mbar_wait_bounded(&d3full[buf], (nc / 3) & 1, 22);   // two uses per tile: parity = use&1
+      for (int nc = 0; nc < L3_CHUNKS; ++nc) {
+        const int buf = nc & 1;
+        tc::mbar_wait_bounded(&d3full[buf], (nc >> 1) & 1, 22);   // two uses per tile: parity = use&1
         tc::fence_after_sync();
-        uint32_t v0[16], v1[16];
-        tc::ld16(lane_base + d3_col(buf) + 32 * h, v0);
-        tc::ld16(lane_base + d3_col(buf) + 32 * h + 16, v1);
+        if (warp == 4) PM_TL(1, 6 + 2 * nc);
+        uint32_t v0[16], v1[16], v2[16];
+        const uint32_t cb = lane_base + COL_D3 + L3_N * buf + 48 * h;
+        tc::ld16(cb, v0);
+        tc::ld16(cb + 16, v1);
+        tc::ld16(cb + 32, v2);
         tc::wait_ld();
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&d3empty[buf]);
         if (valid) {
-          const int co0 = 64 * nc + 32 * h;
+          const int co0 = L3_N * nc + 48 * h;
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             orow[static_cast<size_t>(co0 + i) * P] = fmaf(__uint_as_float(v0[i]), inv3, sh3[co0 + i]);
@@ -346,7 +380,12 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
           for (int i = 0; i < 16; ++i)
             orow[static_cast<size_t>(co0 + 16 + i) * P] =
                 fmaf(__uint_as_float(v1[i]), inv3, sh3[co0 + 16 + i]);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            orow[static_cast<size_t>(co0 + 32 + i) * P] =
+                fmaf(__uint_as_float(v2[i]), inv3, sh3[co0 + 32 + i]);
         }
+        if (warp == 4) PM_TL(1, 7 + 2 * nc);
       }
     }
   }
@@ -354,10 +393,12 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
   __syncthreads();
   if (CL > 1) tc::cluster_sync_all();   // no CTA leaves while peers may still signal its barriers
   if (warp == 2) tc::tmem_dealloc(tm, 512);
+#undef PM_TL
 }
 
 // ---- host-side packing -------------------------------------------------------------------------------
-// fp16 hi/lo images of scale * W[rows r0..r0+nr) x [k0..k0+kt) (row stride ld), K-major no-swizzle.
+// fp16 hi/lo images of scale * W[rows r0..r0+nr) x [k0..k0+kt) (row stride ld), K-major no-swizzle:
+// element (r,k) at (r/8)*SBO + (k/8)*128 + (r%8)*16 + (k%8)*2 with SBO = kt*16.
 static void pack_tile(const float* W, float scale, int ld, int r0, int nr, int k0, int kt,
                       unsigned char* hi, unsigned char* lo) {
   const uint32_t sbo = static_cast<uint32_t>(kt) * 16;
@@ -402,18 +443,20 @@ extern "C" int sonet_pointresnet_tc_pack(const float* W0, int Cin, const float* 
   const float s1 = pow2_scale(W1, static_cast<size_t>(C1) * C0),
               s2 = pow2_scale(W2, static_cast<size_t>(C2) * C1),
               s3 = pow2_scale(W3, static_cast<size_t>(C3) * K3);
+  // layer 1, resident: [128 rows x 64 k]
   pack_tile(W1, s1, C0, 0, C1, 0, C0, blob, blob + W1_BYTES / 2);
   size_t off = W1_BYTES;
-  for (int nc = 0; nc < 4; ++nc) {  // layer 2: [64 rows x 128]
-    pack_tile(W2, s2, C1, 64 * nc, 64, 0, 128, blob + off, blob + off + 16384);
-    off += SLOT_BYTES;
+  // layer 2: four K slabs [256 rows x 32 k]
+  for (int kc = 0; kc < L2_STAGES; ++kc) {
+    pack_tile(W2, s2, C1, 0, C2, L2_KT * kc, L2_KT, blob + off, blob + off + L2_STAGE_BYTES / 2);
+    off += L2_STAGE_BYTES;
   }
-  for (int nc = 0; nc < 6; ++nc)    // layer 3: [64 rows x (128|128|64)]
-    for (int kc = 0; kc < 3; ++kc) {
-      const int kt = (kc < 2) ? 128 : 64;
-      const size_t hb = static_cast<size_t>(64) * kt * 2;
-      pack_tile(W3, s3, K3, 64 * nc, 64, 128 * kc, kt, blob + off, blob + off + hb);
-      off += 2 * hb;
+  // layer 3: four 96-row chunks x five K slabs [96 rows x 64 k]
+  for (int nc = 0; nc < L3_CHUNKS; ++nc)
+    for (int kc = 0; kc < L3_KSTAGES; ++kc) {
+      pack_tile(W3, s3, K3, L3_N * nc, L3_N, L3_KT * kc, L3_KT, blob + off,
+                blob + off + L3_STAGE_BYTES / 2);
+      off += L3_STAGE_BYTES;
     }
   if (off != static_cast<size_t>(BLOB_BYTES)) SONET_FAIL(SONET_ERR_BAD_ARG, "pack: size mismatch");
   float* f = fparams_host;
@@ -431,9 +474,9 @@ extern "C" int sonet_pointresnet_tc_pack(const float* W0, int Cin, const float* 
   return SONET_OK;
 }
 
-extern "C" int sonet_pointresnet_tc_forward(const float* x, int Cin, int B, int P, const void* blob,
-                                            const float* fparams, float* out,
-                                            sonet_stream_t stream) {
+static int launch_pointresnet_tc(const float* x, int Cin, int B, int P, const void* blob,
+                                 const float* fparams, float* out, long long* dbg,
+                                 sonet_stream_t stream) {
   using namespace sonet;
   using namespace sonet::pm;
   SONET_REQUIRE(B >= 0 && P >= 0, "pointresnet_tc: negative dimension");
@@ -445,12 +488,12 @@ extern "C" int sonet_pointresnet_tc_forward(const float* x, int Cin, int B, int 
   SONET_REQUIRE(tiles < (1LL << 31), "pointresnet_tc: too many tiles");
   SONET_REQUIRE(SMEM_BYTES <= max_smem_optin(), "pointresnet_tc: needs %d B of shared memory",
                 SMEM_BYTES);
-  // cluster size: 2 by default (148 SMs = 74 pairs, no stranded SMs); SONET_TC_CLUSTER=1|2|4
+  // cluster size: 1 by default; SONET_TC_CLUSTER=2|4 enables the multicast weight stream
   static int cl_env = -1;
   if (cl_env < 0) {
     const char* e = getenv("SONET_TC_CLUSTER");
-    cl_env = e ? atoi(e) : 2;
-    if (cl_env != 1 && cl_env != 2 && cl_env != 4) cl_env = 2;
+    cl_env = e ? atoi(e) : 1;
+    if (cl_env != 1 && cl_env != 2 && cl_env != 4) cl_env = 1;
   }
   int cl = cl_env;
   const int sms = sm_count();
@@ -472,6 +515,20 @@ extern "C" int sonet_pointresnet_tc_forward(const float* x, int Cin, int B, int 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, kern, x, Cin, B, P, static_cast<const unsigned char*>(blob), fparams, out);
+  cudaLaunchKernelEx(&cfg, kern, x, Cin, B, P, static_cast<const unsigned char*>(blob), fparams, out,
+                     dbg);
   return check_launch("pointresnet_tc");
+}
+
+extern "C" int sonet_pointresnet_tc_forward(const float* x, int Cin, int B, int P, const void* blob,
+                                            const float* fparams, float* out,
+                                            sonet_stream_t stream) {
+  return launch_pointresnet_tc(x, Cin, B, P, blob, fparams, out, nullptr, stream);
+}
+
+extern "C" int sonet_debug_pointresnet_tc_timeline(const float* x, int Cin, int B, int P,
+                                                   const void* blob, const float* fparams,
+                                                   float* out, long long* timeline64,
+                                                   sonet_stream_t stream) {
+  return launch_pointresnet_tc(x, Cin, B, P, blob, fparams, out, timeline64, stream);
 }

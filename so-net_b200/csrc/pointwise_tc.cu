@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ========== MMA issuer: converged warp, elect.sync issues from one lane ==========
+    {
       const uint32_t a_base = smem_u32(smem + OFF_A), w_base = smem_u32(smem + OFF_W);
       uint32_t q = 0;
       for (int it = 0; it < my_items; ++it) {
@@ -142,13 +142,13 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
                            al = tc::smem_desc(as + A_BYTES / 2 + ks * 256, 128, 1024),
                            bh = tc::smem_desc(ws + ks * 256, 128, 1024),
                            bl = tc::smem_desc(ws + nw * KCH * 2 + ks * 256, 128, 1024);
-            tc::mma_ss(dcol, ah, bh, idesc, (kc | ks) != 0);
-            tc::mma_ss(dcol, al, bh, idesc, 1);
-            tc::mma_ss(dcol, ah, bl, idesc, 1);
+            tc::mma_ss_elect(dcol, ah, bh, idesc, (kc | ks) != 0);
+            tc::mma_ss_elect(dcol, al, bh, idesc, 1);
+            tc::mma_ss_elect(dcol, ah, bl, idesc, 1);
           }
-          tc::commit(&empty[slot]);
+          tc::commit_elect(&empty[slot]);
         }
-        tc::commit(&d_full[buf]);
+        tc::commit_elect(&d_full[buf]);
       }
     }
   } else if (warp >= 8) {

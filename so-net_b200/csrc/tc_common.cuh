@@ -116,6 +116,55 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       : "memory");
 }
 
+// ---- warp-converged issue: every lane of the (converged) MMA warp calls these with warp-uniform
+// operands; elect.sync picks one lane that actually issues. Issuing from inside a divergent
+// `if (lane == 0)` region instead makes nvcc wrap every UTCHMMA in an ELECT/BRA uniformisation
+// loop (~100 cycles per MMA, measured: the kernel became issue-bound).
+__device__ __forceinline__ void mma_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, e;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ss_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, e;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void commit_multicast_elect(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
 // ---- TMEM <-> registers: 32x32b shape = each thread its own lane, N consecutive 32-bit columns ----
 __device__ __forceinline__ void ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(

@@ -52,6 +52,8 @@ _SIGNATURES = {
     "sonet_pointwise_tc_forward": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                                    ctypes.c_float, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                    c_int, c_void_p, c_void_p],
+    "sonet_debug_pointresnet_tc_timeline": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                            c_void_p, c_void_p, c_void_p],
     "sonet_debug_tc_probe": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                              c_void_p],
     "sonet_last_error_string": [],

@@ -33,13 +33,13 @@ def test_pack_images_round_trip(lib_built):
     tol = 2.0 ** -20
     w1 = unpack(0, 128, 64, 16384) * inv[0]
     assert np.abs(w1 - W[1].numpy()).max() <= tol * np.abs(W[1].numpy()).max()
-    # layer-2 chunk 3 (rows 192..255) is the 4th streamed stage
-    w2c = unpack(32768 + 3 * 32768, 64, 128, 16384) * inv[1]
-    assert np.abs(w2c - W[2].numpy()[192:256]).max() <= tol * np.abs(W[2].numpy()).max()
-    # layer-3 chunk 1, K slab 2 (rows 64..127, k 256..319): stage 4 + 3 + 2
-    base = 32768 + 4 * 32768 + (32768 * 2 + 16384) + 2 * 32768
-    w3c = unpack(base, 64, 64, 8192) * inv[2]
-    assert np.abs(w3c - W[3].numpy()[64:128, 256:320]).max() <= tol * np.abs(W[3].numpy()).max()
+    # layer 2 streams four K slabs [256 rows x 32 k]; slab 3 (k 96..127) is the 4th stage
+    w2c = unpack(32768 + 3 * 32768, 256, 32, 16384) * inv[1]
+    assert np.abs(w2c - W[2].numpy()[:, 96:128]).max() <= tol * np.abs(W[2].numpy()).max()
+    # layer 3 streams [96 rows x 64 k] stages, chunk-major: chunk 1 (rows 96..191), slab 4 (k 256..319)
+    base = 32768 + 4 * 32768 + (1 * 5 + 4) * 24576
+    w3c = unpack(base, 96, 64, 12288) * inv[2]
+    assert np.abs(w3c - W[3].numpy()[96:192, 256:320]).max() <= tol * np.abs(W[3].numpy()).max()
     assert np.array_equal(f[:384].reshape(64, 6), W[0].numpy())
     assert np.array_equal(f[384:448], sh[0].numpy())
     assert np.array_equal(f[448 + 128 + 256:448 + 128 + 256 + 384], sh[3].numpy())
