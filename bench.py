@@ -215,7 +215,7 @@ def kernel_report(profile_steps, peaks):
             row.update(bound="tensor", achieved=round(ach, 3), peak=tf, unit="TFLOP/s",
                        frac=round(ach / tf, 5), shape="[%d,%d+%d,%d]->%d" % (B, C0, C1, P, Cout),
                        note="fp32 CUDA-core path vs the bf16 tensor peak")
-        elif key.startswith("pointresnet_tc_forward"):
+        elif key.startswith("pointresnet_tc_forward") or key.startswith("pointresnet_tc_pool_forward"):
             Bc, P = a[2], a[3]
             flops = 328448.0 * Bc * P          # 2 * (6*64 + 64*128 + 128*256 + 320*384)
             ach = flops / (ms * 1e-3) / 1e12
@@ -223,7 +223,9 @@ def kernel_report(profile_steps, peaks):
                        frac=round(ach / tf, 4), executed_tflops=round(3 * ach, 1),
                        shape="[%d,%d,%d] 6->64->128->256->[320]->384" % (Bc, a[1], P),
                        note="algorithmic flops; the fp16 hi/lo split executes 3x as many on "
-                            "the tensor pipe, so frac <= 0.33 by construction")
+                            "the tensor pipe, so frac <= 0.33 by construction"
+                            + ("; per-node max fused into the epilogue (first_pn_out never "
+                               "written)" if "pool" in key else ""))
         elif key.startswith("index_max"):
             B, C, N, K = a[2], a[3], a[4], a[5]
             byts = 4.0 * B * C * N + 4.0 * B * N + 4.0 * B * C * K * (2 if a[7] else 1)
@@ -369,6 +371,35 @@ def main():
                 "ms": dom["ms"], "share_of_step": round(dom["ms"] / kernel_ms, 4),
                 "note": dom.get("note")}
 
+    # the plugin op the reference ships (index_max) no longer runs inside the classifier step (its
+    # max is fused into the MLP epilogue): time it standalone on the cfg-2 tensor for its roofline
+    standalone = []
+    if rank == 0:
+        g = torch.Generator(device=dev).manual_seed(0)
+        data = torch.randn(B, 384, K_NN * NPTS, device=dev, generator=g)
+        index = torch.randint(0, M_NODES, (B, K_NN * NPTS), device=dev, generator=g,
+                              dtype=torch.int32)
+        for _ in range(3):
+            ops.index_max(data, index, M_NODES, with_values=True)
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.index_max(data, index, M_NODES, with_values=True)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms_im = sum(ts) / len(ts)
+        byts = 4.0 * B * 384 * K_NN * NPTS + 4.0 * B * K_NN * NPTS + 8.0 * B * 384 * M_NODES
+        standalone.append({"kernel": "index_max_f32 (standalone, [64,384,15000] K=64)",
+                           "ms": round(ms_im, 4), "bound": "hbm",
+                           "achieved": round(byts / (ms_im * 1e-3) / 1e9, 1),
+                           "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                           "frac": round(byts / (ms_im * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                           "traffic": NCU_TRAFFIC.get("index_max_f32")})
+        del data, index
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = cpu_arm(steps=3, warmup=1)
@@ -386,6 +417,7 @@ def main():
                         "d2h_bytes_per_step": d2h_bytes * world},
                 "gpu_launches": launches, "wall_s_timed_region": round(wall, 4),
                 "clocks": clocks, "roofline": roofline, "kernels": kernels,
+                "standalone_kernels": standalone,
                 "cpu_baseline": cpu_baseline,
                 "checksum": float(out.double().sum().item())}
         print(json.dumps(line))

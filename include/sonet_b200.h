@@ -180,6 +180,32 @@ int sonet_pointresnet_tc_pack(const float* W0, int Cin, const float* W1, const f
 int sonet_pointresnet_tc_forward(const float* x, int Cin, int B, int P, const void* blob,
                                  const float* fparams, float* out, sonet_stream_t stream);
 
+/* ---- a-3 + a-5 + a-6/a-7 fused: node-sorted copies -> tcgen05 PointResNet -> per-node max -----
+ * The classifier / auto-encoder path, where first_pn_out [B,384,kN] itself is never needed
+ * (models/networks.py:168-185): it is neither written nor re-read.
+ *   sonet_som_sort_decenter: buckets the k*N stacked copies of each cloud by node (order inside a
+ *     node arbitrary) and writes, in that order, x_sorted [B,3(+3),kN] = decentred coordinates
+ *     (+ normals), node_sorted [B,kN] i32 and pos0 [B] = sorted position of stacked copy 0.
+ *     count [B,M] is sonet_som_assign's output.
+ *   sonet_pointresnet_tc_pool_forward: as sonet_pointresnet_tc_forward on x_sorted, but instead of
+ *     `out` it max-reduces every channel per node into pool_keys [B,384,M] i32 (order-preserving
+ *     keys; must hold sonet_pool_keys_init()'s value on entry) and writes the 384 features of
+ *     stacked copy 0 into p0 [B,384].
+ *   sonet_pool_finalize: keys -> out_val [B,384,M] with the reference's semantics: the node's max
+ *     if some copy exceeded the -1000 sentinel (index_max.cpp:80-81,103), else the feature of
+ *     stacked copy 0 (the idx*mask_row_max gather of networks.py:185); resets the keys. */
+int sonet_som_sort_decenter(const float* x, const float* sn, const float* cluster_mean,
+                            const int32_t* min_idx_i32, const int32_t* count, int B, int N, int M,
+                            int k, float* x_sorted, int32_t* node_sorted, int32_t* pos0,
+                            sonet_stream_t stream);
+int sonet_pointresnet_tc_pool_forward(const float* x_sorted, int Cin, int B, int P, const void* blob,
+                                      const float* fparams, const int32_t* node_sorted,
+                                      const int32_t* pos0, int M, int32_t* pool_keys, float* p0,
+                                      sonet_stream_t stream);
+int sonet_pool_keys_init(int32_t* keys, long long n, sonet_stream_t stream);
+int sonet_pool_finalize(int32_t* keys, const float* p0, int B, int C, int M, float* out_val,
+                        sonet_stream_t stream);
+
 /* ---- a-8/a-9/a-10 on tensor cores: generic point-wise layer on tcgen05 --------------------------
  * Same contract as sonet_pointwise_layer_f32 (EquivariantLayer / MyConv2d 1x1 eval forward,
  * models/layers.py:203-210, 282-296) for layers dense enough for tensor cores (KNNModule,

@@ -84,11 +84,27 @@ __device__ __forceinline__ uint64_t bdesc(uint32_t saddr, uint32_t sbo) {
 // fetches 1/CL of every stage from L2 and multicasts it into all CL shared memories. Measured: no
 // gain at CL=2 and a loss at CL=4 (the stream is not the bound; lockstep coupling costs), so the
 // default is CL=1; kept as a tested option (SONET_TC_CLUSTER).
-template <int CL>
+//
+// POOL variant (the classifier / auto-encoder path): the input rows are the stacked copies SORTED
+// BY NODE (csrc/som_sort.cu) and the layer-3 epilogue, instead of storing the 384 channels of
+// every copy (1.47 GB at B=64,N=5000) for a separate index_max launch to re-read, reduces them
+// per node right away: lanes of a warp that share a node do one `redux.sync.max` on an
+// order-preserving integer key and the group leader one `red.global.max` into pool[b,c,node]
+// (models/index_max_ext semantics are restored by pool_finalize_kernel). first_pn_out is never
+// written.
+struct PoolArgs {
+  const int32_t* node_sorted;  // [B,P] node id of each sorted row
+  const int32_t* pos0;         // [B] sorted row of stacked copy 0
+  int32_t* keys;               // [B,384,M] running max keys (POOL_KEY_INIT when untouched)
+  float* p0;                   // [B,384] features of stacked copy 0
+  int M;
+};
+
+template <int CL, bool POOL>
 __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
     pointresnet_tc_kernel(const float* __restrict__ x_in, int Cin, int B, int P,
                           const unsigned char* __restrict__ blob, const float* __restrict__ fparams,
-                          float* __restrict__ out, long long* __restrict__ dbg) {
+                          float* __restrict__ out, long long* __restrict__ dbg, PoolArgs pool) {
   using namespace pm;
   // optional timeline (debug entry point only): clock64 at phase boundaries of CTA 0's 4th tile
 #define PM_TL(role, idx)                                                          \
@@ -356,7 +372,38 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
       if (warp == 4) PM_TL(1, 5);
 
       // ---- layer 3 epilogue: four chunks of 96 channels, 48 per warpgroup; bare layer (no ReLU) ----
-      float* orow = out + (static_cast<size_t>(b) * C3) * P + j;
+      float* orow = POOL ? nullptr : out + (static_cast<size_t>(b) * C3) * P + j;
+      // POOL: lanes sharing a node form a group (rows are node-sorted: 1-2 groups per warp)
+      // (full-mask redux + a warp-uniform mode: a redux over match_any masks makes nvcc emit a
+      // per-group uniformisation loop, measured 2x slower than not fusing at all)
+      constexpr int POOL_KEY_MIN = static_cast<int>(0x80000000u);
+      int nd = -1, pmode = -1, laneA = 0, laneB = 0;
+      bool inA = false, inB = false, is_p0 = false, any_p0 = false;
+      int32_t *krow = nullptr, *krowA = nullptr, *krowB = nullptr;
+      if (POOL) {
+        if (valid) nd = __ldg(pool.node_sorted + static_cast<size_t>(b) * P + j);
+        is_p0 = valid && (j == __ldg(pool.pos0 + b));
+        any_p0 = __any_sync(0xffffffffu, is_p0);
+        int32_t* kb = pool.keys + (static_cast<size_t>(b) * C3) * pool.M;
+        krow = kb + max(nd, 0);
+        const unsigned vmask = __ballot_sync(0xffffffffu, nd >= 0);
+        if (vmask != 0) {
+          laneA = __ffs(vmask) - 1;
+          const int nodeA = __shfl_sync(0xffffffffu, nd, laneA);
+          inA = (nd == nodeA);
+          krowA = kb + nodeA;
+          const unsigned rest = vmask & ~__ballot_sync(0xffffffffu, inA);
+          if (rest == 0) {
+            pmode = 0;
+          } else {
+            laneB = __ffs(rest) - 1;
+            const int nodeB = __shfl_sync(0xffffffffu, nd, laneB);
+            inB = (nd == nodeB);
+            krowB = kb + nodeB;
+            pmode = ((rest & ~__ballot_sync(0xffffffffu, inB)) == 0) ? 1 : 2;
+          }
+        }
+      }
       for (int nc = 0; nc < L3_CHUNKS; ++nc) {
         const int buf = nc & 1;
         tc::mbar_wait_bounded(&d3full[buf], (nc >> 1) & 1, 22);   // two uses per tile: parity = use&1
@@ -371,7 +418,58 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&d3empty[buf]);
-        if (valid) {
+        if (POOL) {
+          const int co0 = L3_N * nc + 48 * h;
+          // value -> order-preserving int key; lanes outside `in` contribute the identity
+          auto keyof = [&](uint32_t raw, int co, float& val) {
+            val = fmaf(__uint_as_float(raw), inv3, sh3[co]);
+            const int bits = __float_as_int(val);
+            return bits ^ ((bits >> 31) & 0x7fffffff);
+          };
+          // The 16 per-channel maxima of a group end up lane-distributed (lane i holds channel i;
+          // lanes 16+i the second node's) through selects, then ONE warp-wide red covers them: no
+          // per-channel divergent region (measured: per-channel `if (leader) atomicMax` costs
+          // ~100 cycles each in BSSY/BSYNC reconvergence).
+          auto pool_group = [&](const uint32_t (&v)[16], int cbase) {
+            float vals[16];
+            if (pmode == 0 || pmode == 1) {
+              int mine = POOL_KEY_MIN;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int key = keyof(v[i], cbase + i, vals[i]);
+                const int ma = __reduce_max_sync(0xffffffffu, inA ? key : POOL_KEY_MIN);
+                mine = (lane == i) ? ma : mine;
+                if (pmode == 1) {      // warp-uniform: a node boundary inside the warp
+                  const int mb = __reduce_max_sync(0xffffffffu, inB ? key : POOL_KEY_MIN);
+                  mine = (lane == 16 + i) ? mb : mine;
+                }
+              }
+              const bool second = lane >= 16;
+              if (!second || pmode == 1) {
+                int32_t* dst = (second ? krowB : krowA) +
+                               static_cast<size_t>(cbase + (lane & 15)) * pool.M;
+                atomicMax(dst, mine);
+              }
+            } else if (pmode == 2) {   // three or more nodes in one warp (tiny nodes): per lane
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int key = keyof(v[i], cbase + i, vals[i]);
+                if (nd >= 0) atomicMax(krow + static_cast<size_t>(cbase + i) * pool.M, key);
+              }
+            }
+            if (any_p0) {              // warp-uniform and rare: one warp per cloud and column half
+              if (is_p0) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  pool.p0[static_cast<size_t>(b) * C3 + cbase + i] =
+                      fmaf(__uint_as_float(v[i]), inv3, sh3[cbase + i]);
+              }
+            }
+          };
+          pool_group(v0, co0);
+          pool_group(v1, co0 + 16);
+          pool_group(v2, co0 + 32);
+        } else if (valid) {
           const int co0 = L3_N * nc + 48 * h;
 #pragma unroll
           for (int i = 0; i < 16; ++i)
@@ -476,13 +574,15 @@ extern "C" int sonet_pointresnet_tc_pack(const float* W0, int Cin, const float* 
 
 static int launch_pointresnet_tc(const float* x, int Cin, int B, int P, const void* blob,
                                  const float* fparams, float* out, long long* dbg,
-                                 sonet_stream_t stream) {
+                                 const sonet::PoolArgs* pool, sonet_stream_t stream) {
   using namespace sonet;
   using namespace sonet::pm;
   SONET_REQUIRE(B >= 0 && P >= 0, "pointresnet_tc: negative dimension");
   SONET_REQUIRE(Cin >= 1 && Cin <= 6, "pointresnet_tc: Cin=%d out of range [1,6]", Cin);
   if (B == 0 || P == 0) return SONET_OK;
-  SONET_REQUIRE(x && blob && fparams && out, "pointresnet_tc: null pointer");
+  SONET_REQUIRE(x && blob && fparams && (out || pool), "pointresnet_tc: null pointer");
+  SONET_REQUIRE(!pool || (pool->node_sorted && pool->pos0 && pool->keys && pool->p0 && pool->M >= 1),
+                "pointresnet_tc: incomplete pool arguments");
   SONET_REQUIRE(aligned16(blob), "pointresnet_tc: weight blob must be 16-byte aligned");
   const long long tiles = static_cast<long long>(B) * ((P + TILE - 1) / TILE);
   SONET_REQUIRE(tiles < (1LL << 31), "pointresnet_tc: too many tiles");
@@ -495,13 +595,15 @@ static int launch_pointresnet_tc(const float* x, int Cin, int B, int P, const vo
     cl_env = e ? atoi(e) : 1;
     if (cl_env != 1 && cl_env != 2 && cl_env != 4) cl_env = 1;
   }
-  int cl = cl_env;
+  int cl = pool ? 1 : cl_env;
   const int sms = sm_count();
   while (cl > 1 && (tiles < cl || sms % cl != 0)) cl >>= 1;
   int grid = static_cast<int>(std::min<long long>(tiles, sms));
   grid -= grid % cl;
-  auto kern = cl == 4 ? pointresnet_tc_kernel<4>
-                      : (cl == 2 ? pointresnet_tc_kernel<2> : pointresnet_tc_kernel<1>);
+  auto kern = pool ? pointresnet_tc_kernel<1, true>
+                   : (cl == 4 ? pointresnet_tc_kernel<4, false>
+                              : (cl == 2 ? pointresnet_tc_kernel<2, false>
+                                         : pointresnet_tc_kernel<1, false>));
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -515,20 +617,30 @@ static int launch_pointresnet_tc(const float* x, int Cin, int B, int P, const vo
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  PoolArgs pa = pool ? *pool : PoolArgs{nullptr, nullptr, nullptr, nullptr, 0};
   cudaLaunchKernelEx(&cfg, kern, x, Cin, B, P, static_cast<const unsigned char*>(blob), fparams, out,
-                     dbg);
+                     dbg, pa);
   return check_launch("pointresnet_tc");
 }
 
 extern "C" int sonet_pointresnet_tc_forward(const float* x, int Cin, int B, int P, const void* blob,
                                             const float* fparams, float* out,
                                             sonet_stream_t stream) {
-  return launch_pointresnet_tc(x, Cin, B, P, blob, fparams, out, nullptr, stream);
+  return launch_pointresnet_tc(x, Cin, B, P, blob, fparams, out, nullptr, nullptr, stream);
+}
+
+extern "C" int sonet_pointresnet_tc_pool_forward(const float* x_sorted, int Cin, int B, int P,
+                                                 const void* blob, const float* fparams,
+                                                 const int32_t* node_sorted, const int32_t* pos0,
+                                                 int M, int32_t* pool_keys, float* p0,
+                                                 sonet_stream_t stream) {
+  sonet::PoolArgs pa{node_sorted, pos0, pool_keys, p0, M};
+  return launch_pointresnet_tc(x_sorted, Cin, B, P, blob, fparams, nullptr, nullptr, &pa, stream);
 }
 
 extern "C" int sonet_debug_pointresnet_tc_timeline(const float* x, int Cin, int B, int P,
                                                    const void* blob, const float* fparams,
                                                    float* out, long long* timeline64,
                                                    sonet_stream_t stream) {
-  return launch_pointresnet_tc(x, Cin, B, P, blob, fparams, out, timeline64, stream);
+  return launch_pointresnet_tc(x, Cin, B, P, blob, fparams, out, timeline64, nullptr, stream);
 }

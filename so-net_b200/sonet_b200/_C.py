@@ -47,6 +47,12 @@ _SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p],
     "sonet_pointresnet_tc_forward": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                      c_void_p],
+    "sonet_som_sort_decenter": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sonet_pointresnet_tc_pool_forward": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    "sonet_pool_keys_init": [c_void_p, ctypes.c_longlong, c_void_p],
+    "sonet_pool_finalize": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "sonet_pointwise_tc_blob_bytes": [c_int, c_int],
     "sonet_pointwise_tc_pack": [c_void_p, c_int, c_int, c_void_p, c_void_p],
     "sonet_pointwise_tc_forward": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,

@@ -434,10 +434,10 @@ class PointResNet(nn.Module):
                              last_extra_in=out_channels_list[0])
 
     # ---- fused tcgen05 path (csrc/pointmlp_tc.cu): the encoder's first PointResNet -------------
-    def _tc_eligible(self, x, x1):
+    def _tc_eligible(self, cin, x1):
         if x1 is not None or os.environ.get("SONET_TC", "1") == "0":
             return False
-        if list(self.out_channels_list) != [64, 128, 256, 384] or x.shape[1] > 6:
+        if list(self.out_channels_list) != [64, 128, 256, 384] or cin > 6:
             return False
         ls = self.layers
         return (all(l.normalization == 'batch' and l.activation == 'relu' for l in ls[:3])
@@ -463,7 +463,7 @@ class PointResNet(nn.Module):
         n = len(self.out_channels_list)
         first, last = self.layers[0], self.layers[n - 1]
         if first.fast(x) and x.dim() == 3 and all(l.fast(x) for l in self.layers) \
-                and self._tc_eligible(x, x1):
+                and self._tc_eligible(x.shape[1], x1):
             blob, fpar = self._tc_params()
             return ops.pointresnet_tc(x.contiguous(), blob, fpar)
         if first.fast(x) and x.dim() == 3 and all(l.fast(x) for l in self.layers):

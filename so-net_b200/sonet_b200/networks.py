@@ -84,6 +84,13 @@ class Encoder(nn.Module):
         self._assign = None
         self._mask = None
         self._centers = None
+        self._x_aug = None
+        self._first_pn_out = None
+        self._lazy_src = None
+        # True (default): when first_pn_out itself is not needed, fuse the per-node max into the
+        # tcgen05 PointResNet and never write it. Callers that read encoder.first_pn_out every
+        # forward (the segmenter) set this to False to avoid the lazy recomputation.
+        self.fuse_pool = True
 
     # ---- lazily materialised public attributes (API of models/networks.py:127, 169) -----------
     @property
@@ -100,6 +107,28 @@ class Encoder(nn.Module):
             self._centers = ops.gather_points(self.som_node.detach().contiguous(),
                                               self._assign["min_idx_i32"])
         return self._centers
+
+    def _materialise_x_aug(self):
+        if self._x_aug is None and self._lazy_src is not None:
+            xd, snd, idx32, k, _ = self._lazy_src
+            self._x_aug, _ = ops.som_decenter(xd, snd, self.som_node.detach(), idx32, k)
+        return self._x_aug
+
+    @property
+    def x_decentered(self):
+        """[B,3,kN] stacked points minus their node centre (models/networks.py:171)."""
+        xa = self._materialise_x_aug()
+        return None if xa is None else xa[:, 0:3, :]
+
+    @property
+    def first_pn_out(self):
+        """[B,384,kN] output of the first PointResNet (models/networks.py:176). On the fused
+        path it is only computed when somebody reads it."""
+        if self._first_pn_out is None and self._lazy_src is not None:
+            with torch.no_grad():
+                self._first_pn_out = self.first_pointnet(self._materialise_x_aug(),
+                                                         self._lazy_src[4])
+        return self._first_pn_out
 
     @property
     def min_idx(self):
@@ -128,12 +157,23 @@ class Encoder(nn.Module):
         self.som_builder.node = a["cluster_mean"]
         self.som_node = self.som_builder.node
 
-        if fast:
-            x_aug, _ = ops.som_decenter(xd, sn.detach().contiguous() if use_sn else None,
-                                        self.som_node, idx32, k)
-            self.x_decentered = x_aug[:, 0:3, :]
-            self.first_pn_out = self.first_pointnet(x_aug, epoch)
-            _, self.first_pn_out_masked_max = ops.index_max(self.first_pn_out, idx32, M,
+        snd = sn.detach().contiguous() if use_sn else None
+        self._lazy_src = (xd, snd, idx32, k, epoch)
+        self._x_aug, self._first_pn_out = None, None
+        fpn = self.first_pointnet
+        if (fast and self.fuse_pool and M <= 256 and fpn.layers[0].fast(xd)
+                and fpn._tc_eligible(6 if use_sn else 3, None)):
+            # fused path: node-sorted copies -> tcgen05 PointResNet -> per-node max. Neither
+            # x_augmented nor first_pn_out [B,384,kN] is materialised (they stay available as
+            # lazily recomputed attributes for callers that read them).
+            xs, ns, p0 = ops.som_sort_decenter(xd, snd, self.som_node, idx32, a["count"], k)
+            blob, fpar = fpn._tc_params()
+            self.first_pn_out_masked_max = ops.pointresnet_tc_pool(xs, blob, fpar, ns, p0, M)
+        elif fast:
+            x_aug, _ = ops.som_decenter(xd, snd, self.som_node, idx32, k)
+            self._x_aug = x_aug
+            self._first_pn_out = self.first_pointnet(x_aug, epoch)
+            _, self.first_pn_out_masked_max = ops.index_max(self._first_pn_out, idx32, M,
                                                             with_values=True)
         else:
             # differentiable composition (training): same math with gathers instead of the
@@ -142,14 +182,12 @@ class Encoder(nn.Module):
             centers = torch.gather(self.som_node, 2, idx64.unsqueeze(1).expand(-1, 3, -1))
             self._centers = centers.detach()
             x_stack = torch.cat((x,) * k, dim=2)
-            self.x_decentered = (x_stack - self._centers).detach()
-            if use_sn:
-                x_in = torch.cat((self.x_decentered, torch.cat((sn,) * k, dim=2)), dim=1)
-            else:
-                x_in = self.x_decentered
-            self.first_pn_out = self.first_pointnet(x_in, epoch)
-            gather_index = ops.index_max(self.first_pn_out.detach().contiguous(), idx32, M).long()
-            self.first_pn_out_masked_max = self.first_pn_out.gather(
+            x_dec = (x_stack - self._centers).detach()
+            x_in = torch.cat((x_dec, torch.cat((sn,) * k, dim=2)), dim=1) if use_sn else x_dec
+            self._x_aug = x_in
+            self._first_pn_out = self.first_pointnet(x_in, epoch)
+            gather_index = ops.index_max(self._first_pn_out.detach().contiguous(), idx32, M).long()
+            self.first_pn_out_masked_max = self._first_pn_out.gather(
                 dim=2, index=gather_index * mask_row_max.unsqueeze(1).long())
 
         if opt.som_k >= 2:

@@ -321,3 +321,54 @@ def pointwise_layer_tc(x0, blob, inv_scale, shift, cout, relu, x1=None, addend=N
               float(inv_scale), _C.ptr(shift), int(cout), int(bool(relu)), _C.ptr(addend),
               _C.ptr(gidx), G, _C.ptr(out), _stream(x0))
     return out
+
+
+def som_sort_decenter(x, sn, cluster_mean, min_idx_i32, count, k):
+    """-> (x_sorted [B,3(+3),kN], node_sorted [B,kN] i32, pos0 [B] i32): the stacked copies grouped
+    by node, decentred (models/networks.py:168-172) — input of pointresnet_tc_pool."""
+    _chk(x, "x", torch.float32)
+    _chk(sn, "sn", torch.float32, optional=True)
+    _chk(cluster_mean, "cluster_mean", torch.float32)
+    _chk(min_idx_i32, "min_idx", torch.int32)
+    _chk(count, "count", torch.int32)
+    B, _, N = x.shape
+    M = cluster_mean.shape[2]
+    kN = k * N
+    dev = x.device
+    with torch.cuda.device(dev):
+        xs = torch.empty((B, 6 if sn is not None else 3, kN), dtype=torch.float32, device=dev)
+        ns = torch.empty((B, kN), dtype=torch.int32, device=dev)
+        p0 = torch.empty((B,), dtype=torch.int32, device=dev)
+        _call("sonet_som_sort_decenter", _C.ptr(x), _C.ptr(sn), _C.ptr(cluster_mean),
+              _C.ptr(min_idx_i32), _C.ptr(count), B, N, M, int(k), _C.ptr(xs), _C.ptr(ns),
+              _C.ptr(p0), _stream(x))
+    return xs, ns, p0
+
+
+_POOL_KEYS = {}   # (device, B, M) -> persistent key buffer (self-resetting: finalize re-inits it)
+
+
+def pointresnet_tc_pool(x_sorted, blob, fparams, node_sorted, pos0, M):
+    """Fused tcgen05 PointResNet + per-node max: -> first_pn_out_masked_max [B,384,M]."""
+    _chk(x_sorted, "x_sorted", torch.float32)
+    _chk(blob, "blob", torch.uint8)
+    _chk(fparams, "fparams", torch.float32)
+    _chk(node_sorted, "node_sorted", torch.int32)
+    _chk(pos0, "pos0", torch.int32)
+    B, Cin, P = x_sorted.shape
+    dev = x_sorted.device
+    with torch.cuda.device(dev):
+        kk = (dev, B, int(M))
+        keys = _POOL_KEYS.get(kk)
+        if keys is None:
+            keys = torch.empty((B, 384, M), dtype=torch.int32, device=dev)
+            _call("sonet_pool_keys_init", _C.ptr(keys), keys.numel(), _stream(x_sorted))
+            _POOL_KEYS[kk] = keys
+        p0 = torch.empty((B, 384), dtype=torch.float32, device=dev)
+        out = torch.empty((B, 384, M), dtype=torch.float32, device=dev)
+        _call("sonet_pointresnet_tc_pool_forward", _C.ptr(x_sorted), Cin, B, P, _C.ptr(blob),
+              _C.ptr(fparams), _C.ptr(node_sorted), _C.ptr(pos0), int(M), _C.ptr(keys), _C.ptr(p0),
+              _stream(x_sorted))
+        _call("sonet_pool_finalize", _C.ptr(keys), _C.ptr(p0), B, 384, int(M), _C.ptr(out),
+              _stream(x_sorted))
+    return out

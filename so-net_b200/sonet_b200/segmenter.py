@@ -15,6 +15,7 @@ class Model():
         dev = opt.device
         self.encoder = networks.Encoder(opt).to(dev)
         self.segmenter = networks.Segmenter(opt).to(dev)
+        self.encoder.fuse_pool = False   # the head reads first_pn_out of every forward
 
         B, N, M = opt.batch_size, opt.input_pc_num, opt.node_num
         self.input_pc = torch.empty(B, 3, N, dtype=torch.float32, device=dev)

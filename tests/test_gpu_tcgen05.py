@@ -146,3 +146,57 @@ def test_pointwise_tc_gathered_addend():
     got = ops.pointwise_layer_tc(x0.to(DEV), blob.to(DEV), inv, None, Cout, True,
                                  addend=add.to(DEV), gidx=gidx.to(DEV))
     assert_close(got, want, "tcgen05 layer + gathered addend", 2e-5)
+
+
+# ---- fused pool path: node-sorted copies -> tcgen05 PointResNet -> per-node max ---------------------
+@pytest.mark.parametrize("B,N,mode", [(3, 1024, "sampled"), (2, 700, "uniform"), (2, 5000, "sampled")])
+def test_fused_pool_matches_unfused_path(B, N, mode, monkeypatch):
+    """first_pn_out_masked_max from the fused kernel == index_max(+gather) over the materialised
+    first_pn_out of the same tcgen05 PointResNet (bit-exact: same MMAs, max is order-free), incl.
+    empty nodes (feature of stacked copy 0) — models/networks.py:181-185."""
+    from sonet_b200 import ops, synth
+    monkeypatch.setenv("SONET_TC", "1")
+    net = _resnet(6, seed=N).to(DEV)
+    inp = synth.synth_inputs(B, N, 64, seed=N, node_mode=mode)
+    x, sn, node = inp["pc"].to(DEV), inp["sn"].to(DEV), inp["node"].to(DEV)
+    if mode == "uniform":
+        node[:, :, 3:9] += 50.0          # six nodes nobody is near: empty nodes
+    a = ops.som_assign(x, node, 3)
+    if mode == "uniform":
+        assert int((a["count"] == 0).sum()) >= 6 * B, "case must exercise empty nodes"
+    with torch.no_grad():
+        x_aug, _ = ops.som_decenter(x, sn, a["cluster_mean"], a["min_idx_i32"], 3)
+        full = net(x_aug)
+        _, want = ops.index_max(full, a["min_idx_i32"], 64, with_values=True)
+        xs, ns, p0 = ops.som_sort_decenter(x, sn, a["cluster_mean"], a["min_idx_i32"], a["count"], 3)
+        blob, fpar = net._tc_params()
+        got = ops.pointresnet_tc_pool(xs, blob, fpar, ns, p0, 64)
+        again = ops.pointresnet_tc_pool(xs, blob, fpar, ns, p0, 64)   # keys self-reset
+    # sorted order really is grouped by node and a permutation of the stacked copies
+    assert bool((ns[:, 1:] >= ns[:, :-1]).all())
+    assert torch.equal(torch.bincount(ns[0].long(), minlength=64), a["count"][0].long())
+    assert torch.equal(got, want)
+    assert torch.equal(again, want)
+
+
+def test_encoder_fused_and_lazy_attributes(monkeypatch):
+    from helpers import assert_close, build_states
+    from sonet_b200 import classifier, synth
+    monkeypatch.setenv("SONET_TC", "1")
+    opt = synth.make_opt("classifier", batch_size=4, input_pc_num=512, device=DEV)
+    st = build_states("classifier", opt, seed=5)
+    inp = synth.synth_inputs(4, 512, seed=5)
+    m = classifier.Model(opt)
+    m.encoder.load_state_dict(st["encoder"])
+    m.classifier.load_state_dict(st["head"])
+    m.set_input(inp["pc"], inp["sn"], inp["label"], inp["node"], inp["node_knn_I"])
+    m.encoder.fuse_pool = True
+    m.test_model()
+    fused = m.score.clone()
+    assert m.encoder._first_pn_out is None                       # never materialised
+    lazy = m.encoder.first_pn_out                                # ... until somebody asks
+    assert lazy.shape == (4, 384, 1536) and m.encoder.x_decentered.shape == (4, 3, 1536)
+    m.encoder.fuse_pool = False
+    m.test_model()
+    assert torch.equal(m.encoder.first_pn_out, lazy)
+    assert_close(fused, m.score, "fused vs unfused scores", 1e-6)
