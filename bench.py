@@ -399,6 +399,31 @@ def main():
                            "frac": round(byts / (ms_im * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
                            "traffic": NCU_TRAFFIC.get("index_max_f32")})
         del data, index
+        # SOM kNN with the API-complete outputs of BatchSOM.query_topk (util/som.py:237-269): top-k
+        # assignment + int64 indices + the dense one-hot mask [B,kN,M] int32 (245 MB): HBM-bound
+        from sonet_b200 import som as som_mod
+        bs = som_mod.BatchSOM(8, 8, 3, dev.index or 0, B)
+        bs.node = model.input_node.detach().clone()
+        for _ in range(3):
+            bs.query_topk(model.pc, K_NN)
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            bs.query_topk(model.pc, K_NN)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms_q = sum(ts) / len(ts)
+        kN = K_NN * NPTS
+        byts = B * (12.0 * NPTS + 12.0 * M_NODES + 8.0 * kN + 4.0 * M_NODES + 4.0 * kN * M_NODES)
+        standalone.append({"kernel": "BatchSOM.query_topk (assign + stats + dense mask), B=64 N=5000",
+                           "ms": round(ms_q, 4), "bound": "hbm",
+                           "achieved": round(byts / (ms_q * 1e-3) / 1e9, 1),
+                           "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                           "frac": round(byts / (ms_q * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                           "traffic": None})
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -68,6 +68,8 @@ int sonet_index_max_cpu_f32(const float* data, const int32_t* index, int B, int 
  *   count       [B,M] i32  = mask_row_sum (models/networks.py:128)
  *   row_max     [B,M] i32  = mask_row_max (count > 0)
  *   cluster_mean[B,3,M] f32 = sum_{assigned copies} x / (count + 1e-5f)   (networks.py:140-142)
+ * count and cluster_mean are nullable together (then no statistics pass runs; row_max, if given,
+ * is still filled — by the assignment kernel itself — which is all BatchSOM.query_topk needs).
  * The per-node sums are accumulated in a fixed order: results are bit-reproducible run to run
  * and independent of how the batch is sharded across GPUs. */
 int sonet_som_assign(const float* x, const float* node, int B, int N, int M, int k,

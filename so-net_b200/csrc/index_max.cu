@@ -139,26 +139,45 @@ __global__ void __launch_bounds__((IM_MAX_WARPS + 1) * 32, 1)
     const bool active = c < C;
     const float* row = data + (static_cast<size_t>(b) * C + (active ? c : 0)) * N;
 
+    // Software pipeline over the row: the loads of group g+1 (IM_UNROLL x 128-bit per lane) are
+    // issued before group g is folded into the table, independent of the index-chunk boundaries —
+    // the first version (loads, then use, per chunk) measured 53 % of HBM with long-scoreboard as
+    // the top stall: not enough bytes in flight.
+    constexpr int GV = 32 * IM_UNROLL;                 // float4 per group and warp
+    constexpr int GPC = IM_CHUNK / 4 / GV;             // groups per index chunk
+    const int nvec_row = N >> 2;
+    const int ngroups = (nvec_row + GV - 1) / GV;
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    float4 nxt[IM_UNROLL];
+    if (active) {
+#pragma unroll
+      for (int u = 0; u < IM_UNROLL; ++u) {
+        const int v = u * 32 + lane;
+        if (v < nvec_row) nxt[u] = ldg_stream_f4(row4 + v);
+      }
+    }
     for (int ch = 0; ch < nch; ++ch) {
       mbar_wait(&full[s], use & 1);
       if (active) {
-        const int n0 = ch * IM_CHUNK;
-        const int nvec = min(IM_CHUNK, N - n0) >> 2;
-        const float4* row4 = reinterpret_cast<const float4*>(row + n0);
         const int4* sidx4 = reinterpret_cast<const int4*>(stage + s * IM_CHUNK);
-        for (int v0 = 0; v0 < nvec; v0 += 32 * IM_UNROLL) {
+        const int g_end = min(ngroups, (ch + 1) * GPC);
+        for (int g = ch * GPC; g < g_end; ++g) {
           float4 d[IM_UNROLL];
 #pragma unroll
-          for (int u = 0; u < IM_UNROLL; ++u) {
-            const int v = v0 + u * 32 + lane;
-            if (v < nvec) d[u] = ldg_stream_f4(row4 + v);
+          for (int u = 0; u < IM_UNROLL; ++u) d[u] = nxt[u];
+          if (g + 1 < ngroups) {
+#pragma unroll
+            for (int u = 0; u < IM_UNROLL; ++u) {
+              const int v = (g + 1) * GV + u * 32 + lane;
+              if (v < nvec_row) nxt[u] = ldg_stream_f4(row4 + v);
+            }
           }
 #pragma unroll
           for (int u = 0; u < IM_UNROLL; ++u) {
-            const int v = v0 + u * 32 + lane;
-            if (v < nvec) {
-              const int4 kk = sidx4[v];
-              const int n = n0 + (v << 2);
+            const int v = g * GV + u * 32 + lane;       // float4 index in the row
+            if (v < nvec_row) {
+              const int4 kk = sidx4[v - ch * (IM_CHUNK / 4)];
+              const int n = v << 2;
               im_update<IdxT>(tval, tidx, lane, K, kk.x, d[u].x, n);
               im_update<IdxT>(tval, tidx, lane, K, kk.y, d[u].y, n + 1);
               im_update<IdxT>(tval, tidx, lane, K, kk.z, d[u].z, n + 2);

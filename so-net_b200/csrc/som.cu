@@ -27,7 +27,8 @@ constexpr int SOM_MAX_K = 4;
 template <int KK>
 __global__ void __launch_bounds__(256)
     som_assign_kernel(const float* __restrict__ x, const float* __restrict__ node, int N, int M,
-                      int32_t* __restrict__ idx32, int64_t* __restrict__ idx64) {
+                      int32_t* __restrict__ idx32, int64_t* __restrict__ idx64,
+                      int32_t* __restrict__ row_flag) {
   __shared__ float4 snode[SOM_MAX_M];
   const int b = blockIdx.y;
   const float* nb = node + static_cast<size_t>(b) * 3 * M;
@@ -74,6 +75,8 @@ __global__ void __launch_bounds__(256)
   for (int s = 0; s < KK; ++s) {
     idx32[o + static_cast<size_t>(s) * N] = bi[s];
     if (idx64 != nullptr) idx64[o + static_cast<size_t>(s) * N] = bi[s];
+    // occupancy flag (mask_row_max) without the statistics pass: every writer stores the same 1
+    if (row_flag != nullptr) row_flag[static_cast<size_t>(b) * M + bi[s]] = 1;
   }
 }
 
@@ -89,16 +92,36 @@ __global__ void __launch_bounds__(STATS_THREADS)
   const float* xb = x + static_cast<size_t>(b) * 3 * N;
   float sx = 0.f, sy = 0.f, sz = 0.f;
   int cnt = 0;
-  // the stacked point order j = s*N + n is the reference's x_stack order (networks.py:132-137)
-  for (int j = threadIdx.x; j < kN; j += STATS_THREADS) {
-    if (ib[j] == m) {
-      int n = j;
-      while (n >= N) n -= N;
-      sx += xb[n];
-      sy += xb[N + n];
-      sz += xb[2 * N + n];
-      ++cnt;
+  // the stacked point order j = s*N + n is the reference's x_stack order (networks.py:132-137).
+  // Per-thread order is fixed (depends only on N), so the sums are bit-reproducible.
+  auto take = [&](int j) {
+    int n = j;
+    while (n >= N) n -= N;
+    sx += xb[n];
+    sy += xb[N + n];
+    sz += xb[2 * N + n];
+    ++cnt;
+  };
+  if ((kN & 3) == 0 && (reinterpret_cast<uintptr_t>(ib) & 15u) == 0) {
+    // 128-bit index loads, 2 in flight per thread: the scan is latency-bound, not bandwidth-bound
+    const int4* ib4 = reinterpret_cast<const int4*>(ib);
+    const int nq = kN >> 2;
+    for (int q0 = threadIdx.x; q0 < nq; q0 += 2 * STATS_THREADS) {
+      const int q1 = q0 + STATS_THREADS;
+      const int4 a = __ldg(ib4 + q0);
+      const int4 c = (q1 < nq) ? __ldg(ib4 + q1) : make_int4(-1, -1, -1, -1);
+      if (a.x == m) take(4 * q0);
+      if (a.y == m) take(4 * q0 + 1);
+      if (a.z == m) take(4 * q0 + 2);
+      if (a.w == m) take(4 * q0 + 3);
+      if (c.x == m) take(4 * q1);
+      if (c.y == m) take(4 * q1 + 1);
+      if (c.z == m) take(4 * q1 + 2);
+      if (c.w == m) take(4 * q1 + 3);
     }
+  } else {
+    for (int j = threadIdx.x; j < kN; j += STATS_THREADS)
+      if (ib[j] == m) take(j);
   }
   __shared__ float rs[3][STATS_THREADS];
   __shared__ int rc[STATS_THREADS];
@@ -199,16 +222,19 @@ extern "C" int sonet_som_assign(const float* x, const float* node, int B, int N,
   SONET_REQUIRE(B <= 65535, "som_assign: B=%d exceeds grid limit", B);
   if (B == 0) return SONET_OK;
   SONET_REQUIRE(x && node && min_idx_i32, "som_assign: null pointer");
-  SONET_REQUIRE((count && row_max && cluster_mean) || (!count && !row_max && !cluster_mean),
-                "som_assign: count/row_max/cluster_mean must be all set or all null");
+  SONET_REQUIRE((count && row_max && cluster_mean) || (!count && !cluster_mean),
+                "som_assign: count and cluster_mean go together (row_max alone is allowed)");
   cudaStream_t st = as_stream(stream);
+  // row_max without statistics (the query_topk API): flags written by the assignment kernel itself
+  int32_t* row_flag = (row_max && !count) ? row_max : nullptr;
+  if (row_flag) cudaMemsetAsync(row_flag, 0, sizeof(int32_t) * static_cast<size_t>(B) * M, st);
   if (N > 0) {
     dim3 grid((N + 255) / 256, B);
     switch (k) {
-      case 1: som_assign_kernel<1><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64); break;
-      case 2: som_assign_kernel<2><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64); break;
-      case 3: som_assign_kernel<3><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64); break;
-      default: som_assign_kernel<4><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64); break;
+      case 1: som_assign_kernel<1><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64, row_flag); break;
+      case 2: som_assign_kernel<2><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64, row_flag); break;
+      case 3: som_assign_kernel<3><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64, row_flag); break;
+      default: som_assign_kernel<4><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64, row_flag); break;
     }
     int rc = check_launch("som_assign");
     if (rc) return rc;

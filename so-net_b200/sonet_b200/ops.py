@@ -79,10 +79,10 @@ def som_assign(x, node, k, want_i64=False, want_stats=True):
     with torch.cuda.device(dev):
         idx32 = torch.empty((B, k * N), dtype=torch.int32, device=dev)
         idx64 = torch.empty((B, k * N), dtype=torch.int64, device=dev) if want_i64 else None
-        count = row_max = cmean = None
+        count = cmean = None
+        row_max = torch.empty((B, M), dtype=torch.int32, device=dev)   # always (cheap flags)
         if want_stats:
             count = torch.empty((B, M), dtype=torch.int32, device=dev)
-            row_max = torch.empty((B, M), dtype=torch.int32, device=dev)
             cmean = torch.empty((B, 3, M), dtype=torch.float32, device=dev)
         _call("sonet_som_assign", _C.ptr(x), _C.ptr(node), B, N, M, int(k), _C.ptr(idx32),
               _C.ptr(idx64), _C.ptr(count), _C.ptr(row_max), _C.ptr(cmean), _stream(x))

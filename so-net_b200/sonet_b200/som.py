@@ -32,7 +32,8 @@ class BatchSOM():
         node = self.node
         if node.shape[0] != x.shape[0]:
             node = node.expand(x.shape[0], node.shape[1], node.shape[2])
-        a = ops.som_assign(x.detach().contiguous(), node.contiguous(), k, want_i64=True)
+        a = ops.som_assign(x.detach().contiguous(), node.contiguous(), k, want_i64=True,
+                           want_stats=False)
         self.last_assignment = a
         mask = ops.som_mask(a["min_idx_i32"], M)
         return mask, a["row_max"], a["min_idx_i64"]
@@ -40,6 +41,6 @@ class BatchSOM():
     def query(self, x):
         """k=1 variant (util/som.py:271-293): (mask [B,N,M] float, mask_row_max [B,M] float)."""
         M = self.rows * self.cols
-        a = ops.som_assign(x.detach().contiguous(), self.node.contiguous(), 1)
+        a = ops.som_assign(x.detach().contiguous(), self.node.contiguous(), 1, want_stats=False)
         self.last_assignment = a
         return ops.som_mask(a["min_idx_i32"], M).float(), a["row_max"].float()
