@@ -76,6 +76,13 @@ int sonet_som_assign(const float* x, const float* node, int B, int N, int M, int
                      int32_t* min_idx_i32, int64_t* min_idx_i64, int32_t* count,
                      int32_t* row_max, float* cluster_mean, sonet_stream_t stream);
 
+/* BatchSOM.query_topk in ONE launch (util/som.py:237-269): assignment + dense one-hot mask
+ * [B,k*N,M] i32 (written by the assignment kernel itself, a coalesced row per store) + mask_row_max
+ * [B,M] i32 + min_idx as int64 (nullable) and int32. HBM-bound: 4*M*k bytes written per point. */
+int sonet_som_query_topk(const float* x, const float* node, int B, int N, int M, int k,
+                         int32_t* mask, int32_t* row_max, int64_t* min_idx_i64,
+                         int32_t* min_idx_i32, sonet_stream_t stream);
+
 /* Dense one-hot mask of the assignment, util/som.py:255-265: mask[b, s*N+n, m] =
  * (min_idx[b,s*N+n]==m), int32 [B,k*N,M]. Pure streaming write (HBM-bound). */
 int sonet_som_mask(const int32_t* min_idx_i32, int B, int kN, int M, int32_t* mask,
@@ -236,6 +243,15 @@ int sonet_pointwise_tc_forward(const float* x0, int C0, const float* x1, int C1,
 int sonet_debug_pointresnet_tc_timeline(const float* x, int Cin, int B, int P, const void* blob,
                                         const float* fparams, float* out, long long* timeline64,
                                         sonet_stream_t stream);
+/* sonet_pointwise_tc_forward (single source, ReLU, no shift) with clock64() stamps of CTA 0 in
+ * timeline128[128] (device): TMA issue / MMA waits+issue / converter / epilogue; tools/tc_timeline.py */
+int sonet_debug_pointwise_tc_timeline(const float* x0, int C0, int B, int P, const void* blob,
+                                      float inv_scale, int Cout, float* out, long long* timeline128,
+                                      sonet_stream_t stream);
+/* Cycles for `iters` back-to-back M=128 x N x 16 fp16 MMAs issued by one CTA: mode 0 = A and B from
+ * shared memory (SS, no-swizzle K-major, 8-row-group stride `sbo`), 1 = A from tensor memory (TS). */
+int sonet_debug_tc_mma_rate(int mode, int N, int sbo, int iters, long long* cycles,
+                            sonet_stream_t stream);
 int sonet_debug_tc_probe(const float* A, const float* Bm, int N, int K, int mode, int layout,
                          int swap_fields, float* D, sonet_stream_t stream);
 

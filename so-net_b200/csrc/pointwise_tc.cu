@@ -9,14 +9,15 @@
 //
 // Rows (b,p) are flattened and tiled by 128 = MMA M = TMEM lanes; an item is (row tile, 256-wide
 // out-channel tile); K streams in 64-channel chunks through a 2-stage ring:
-//   * converter warps (8): read the fp32 activations coalesced along p (thread = row), clamp to the
+//   * converter warps (8): fetch the fp32 activations with cp.async into a staging buffer (thread = row,
+//     coalesced along p, whole chunk in flight), clamp to the
 //     fp16 range, split into fp16 hi/lo and write the K-major no-swizzle A images with one 128-bit
 //     shared store per 8 channels (conflict free), fence.proxy.async, arrive;
 //   * TMA warp: streams the pre-packed fp16 hi/lo weight images (cp.async.bulk + mbarrier);
 //   * MMA warp (one thread): 3 tcgen05.mma.kind::f16 per 16-channel K step (hi*hi + lo*hi + hi*lo),
 //     SS mode, M=128, N<=256, fp32 accumulation in TMEM, two 256-column accumulator buffers so the
 //     epilogue of item i overlaps the MMAs of item i+1;
-//   * epilogue warps (4): tcgen05.ld, fused scale/shift (+ gathered addend) + ReLU, stores with
+//   * epilogue warps (8, two warpgroups split the columns): tcgen05.ld, fused scale/shift (+ gathered addend) + ReLU, stores with
 //     lane = row => 128-byte coalesced along p.
 #include <algorithm>
 #include <cmath>
@@ -30,10 +31,12 @@ constexpr int TILE = 128, KCH = 64, NT = 256;
 constexpr int A_BYTES = 2 * TILE * KCH * 2;   // hi + lo images of the activation chunk, 32 KB
 constexpr int W_BYTES = 2 * NT * KCH * 2;     // hi + lo images of the weight chunk, 64 KB
 constexpr int NSTAGE = 2;
-constexpr int NUM_THREADS = 512;
+constexpr int NUM_THREADS = 640;   // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 4-11 epilogue, 12-19 converters
 constexpr int OFF_A = 0;
 constexpr int OFF_W = OFF_A + NSTAGE * A_BYTES;
-constexpr int OFF_BAR = OFF_W + NSTAGE * W_BYTES;
+constexpr int OFF_STG = OFF_W + NSTAGE * W_BYTES;   // fp32 staging of one activation chunk
+constexpr int STG_BYTES = KCH * TILE * 4;            // [64 ch][128 rows] fp32, 32 KB
+constexpr int OFF_BAR = OFF_STG + STG_BYTES;
 constexpr int NBAR = 3 * NSTAGE + 4;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
@@ -55,8 +58,14 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
     pointwise_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
                         const unsigned char* __restrict__ blob, const float* __restrict__ shift,
                         const float* __restrict__ addend, const int32_t* __restrict__ gidx,
-                        float* __restrict__ out, pwt::Dims d) {
+                        float* __restrict__ out, pwt::Dims d, long long* __restrict__ dbg) {
   using namespace pwt;
+#define PW_TL(role, idx)                                                   \
+  do {                                                                     \
+    if (dbg != nullptr && blockIdx.x == 0 && lane == 0 && (idx) < 32)      \
+      dbg[(role) * 32 + (idx)] = clock64();                                \
+  } while (0)
+  if (dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) dbg[127] = clock64();
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* full_w = bars;                  // [NSTAGE] TMA -> MMA
@@ -82,7 +91,7 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&d_full[i], 1);
-      mbar_init(&d_empty[i], 4);
+      mbar_init(&d_empty[i], 8);
     }
     mbar_fence_init();
   }
@@ -111,6 +120,7 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
           if (use > 0) tc::mbar_wait_bounded(&empty[slot], (use - 1) & 1, 200);
           mbar_arrive_expect_tx(&full_w[slot], bytes);
           bulk_g2s(smem + OFF_W + slot * W_BYTES, blob + off, bytes, &full_w[slot]);
+          if (it == 0) PW_TL(0, kc);
           off += bytes;
         }
       }
@@ -133,8 +143,10 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
         for (int kc = 0; kc < d.kchunks; ++kc, ++q) {
           const uint32_t slot = q % NSTAGE, par = (q / NSTAGE) & 1;
           tc::mbar_wait_bounded(&full_w[slot], par, 202);
+          if (it == 0) PW_TL(1, 3 * kc);
           tc::mbar_wait_bounded(&full_a[slot], par, 203);
           tc::fence_after_sync();
+          if (it == 0) PW_TL(1, 3 * kc + 1);
           const uint32_t as = a_base + slot * A_BYTES, ws = w_base + slot * W_BYTES;
           const int nks = min(4, (d.cin_pad - kc * KCH) / 16);
           for (int ks = 0; ks < nks; ++ks) {
@@ -147,65 +159,90 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
             tc::mma_ss_elect(dcol, ah, bl, idesc, 1);
           }
           tc::commit_elect(&empty[slot]);
+          if (it == 0) PW_TL(1, 3 * kc + 2);
         }
         tc::commit_elect(&d_full[buf]);
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 12) {
     // ================= converters: fp32 activations -> fp16 hi/lo K-major A images =================
-    const int t = threadIdx.x - 256;
+    const int t = threadIdx.x - 384;
     const int m = t & 127, half = t >> 7;   // row in tile; which 32 of the chunk's 64 channels
-    uint32_t q = 0;
-    for (int it = 0; it < my_items; ++it) {
+    // The fp32 activations of a chunk are fetched with cp.async (LDGSTS, 4 B per thread and
+    // channel: a warp copies 128 contiguous bytes) into a staging buffer [64 ch][128 rows]: the
+    // whole 32 KB chunk is in flight without holding registers. (Register-staged loads were
+    // bytes-in-flight bound: 16-32 loads per thread -> 4-5k cycles per chunk in the timeline.)
+    // Every thread later reads back exactly the elements it copied, so cp.async.wait_group is
+    // the only synchronisation needed; the next chunk's copies are issued as soon as the
+    // current values are in registers.
+    const uint32_t total = static_cast<uint32_t>(my_items) * d.kchunks;
+    float* stg = reinterpret_cast<float*>(smem + OFF_STG) + (half * 32) * TILE + m;
+    const uint32_t stg_s = smem_u32(stg);
+    auto issue = [&](uint32_t qq) {
+      const int it = qq / d.kchunks, kc = qq - it * d.kchunks;
       const int item = blockIdx.x + it * gridDim.x;
       const long long R = static_cast<long long>(item / d.ntiles) * TILE + m;
       const bool valid = R < rows;
       const int b = valid ? static_cast<int>(R / d.P) : 0;
       const int p = valid ? static_cast<int>(R - static_cast<long long>(b) * d.P) : 0;
       const float* r0 = x0 + static_cast<size_t>(b) * d.C0 * d.P + p;
-      const float* r1 = d.C1 ? x1 + static_cast<size_t>(b) * d.C1 * d.P + p : nullptr;
-      for (int kc = 0; kc < d.kchunks; ++kc, ++q) {
-        const int c_base = kc * KCH + half * 32;
-        float v[32];
+      const float* r1 = d.C1 ? x1 + static_cast<size_t>(b) * d.C1 * d.P + p : x0;
+      const int c_base = kc * KCH + half * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int ci = c_base + i;
-          float x = 0.f;
-          if (valid && ci < Cin)
-            x = (ci < d.C0) ? __ldg(r0 + static_cast<size_t>(ci) * d.P)
-                            : __ldg(r1 + static_cast<size_t>(ci - d.C0) * d.P);
-          v[i] = fminf(fmaxf(x, -65504.f), 65504.f);
-        }
-        const uint32_t slot = q % NSTAGE, use = q / NSTAGE;
-        if (use > 0) tc::mbar_wait_bounded(&empty[slot], (use - 1) & 1, 204);
-        unsigned char* a_hi = smem + OFF_A + slot * A_BYTES + (m >> 3) * 1024 + (m & 7) * 16;
-#pragma unroll
-        for (int o = 0; o < 4; ++o) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float a = v[o * 8 + 2 * j], c = v[o * 8 + 2 * j + 1];
-            const __half2 h = __floats2half2_rn(a, c);
-            const float2 hf = __half22float2(h);
-            const __half2 l = __floats2half2_rn(a - hf.x, c - hf.y);
-            hi[j] = *reinterpret_cast<const uint32_t*>(&h);
-            lo[j] = *reinterpret_cast<const uint32_t*>(&l);
-          }
-          const int oct = half * 4 + o;
-          *reinterpret_cast<uint4*>(a_hi + oct * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(a_hi + A_BYTES / 2 + oct * 128) =
-              make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_a[slot]);
+      for (int i = 0; i < 32; ++i) {
+        const int ci = c_base + i;
+        const bool ok = valid && ci < Cin;
+        const float* src = !ok ? x0
+                               : (ci < d.C0 ? r0 + static_cast<size_t>(ci) * d.P
+                                            : r1 + static_cast<size_t>(ci - d.C0) * d.P);
+        const uint32_t nbytes = ok ? 4u : 0u;   // 0 -> zero fill
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(stg_s + i * TILE * 4),
+                     "l"(src), "r"(nbytes)
+                     : "memory");
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (total > 0) issue(0);
+    for (uint32_t qq = 0; qq < total; ++qq) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = stg[i * TILE];
+      if (qq + 1 < total) issue(qq + 1);
+      const uint32_t slot = qq % NSTAGE, use = qq / NSTAGE;
+      if (use > 0) tc::mbar_wait_bounded(&empty[slot], (use - 1) & 1, 204);
+      if (warp == 12 && qq < 16) PW_TL(2, 2 * qq);
+      unsigned char* a_hi = smem + OFF_A + slot * A_BYTES + (m >> 3) * 1024 + (m & 7) * 16;
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = fminf(fmaxf(v[o * 8 + 2 * j], -65504.f), 65504.f);
+          const float c = fminf(fmaxf(v[o * 8 + 2 * j + 1], -65504.f), 65504.f);
+          const __half2 h = __floats2half2_rn(a, c);
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn(a - hf.x, c - hf.y);
+          hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+          lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        const int oct = half * 4 + o;
+        *reinterpret_cast<uint4*>(a_hi + oct * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(a_hi + A_BYTES / 2 + oct * 128) =
+            make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_a[slot]);
+      if (warp == 12 && qq < 16) PW_TL(2, 2 * qq + 1);
     }
   } else if (warp >= 4) {
-    // ================= epilogue =================
+    // ================= epilogue: two warpgroups split the item's columns =================
     const int q4 = warp & 3;
+    const int h = (warp - 4) >> 2;
     const int m = q4 * 32 + lane;
     const uint32_t lane_base = tm + (static_cast<uint32_t>(q4 * 32) << 16);
+    const float floor_v = d.relu ? 0.f : -__int_as_float(0x7f800000);   // ReLU as one max
     for (int it = 0; it < my_items; ++it) {
       const int item = blockIdx.x + it * gridDim.x;
       const int nt = item % d.ntiles;
@@ -217,38 +254,50 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
       const int buf = it & 1;
       tc::mbar_wait_bounded(&d_full[buf], (it >> 1) & 1, 205);
       tc::fence_after_sync();
-      float* orow = out + static_cast<size_t>(b) * d.Cout * d.P + p;
+      if (warp == 4 && it < 4) PW_TL(3, 2 * it);
       const float* arow = nullptr;
       if (addend != nullptr && valid) {
         const int g = min(max(__ldg(gidx + R), 0), d.G - 1);
         arow = addend + static_cast<size_t>(b) * d.Cout * d.G + g;
       }
-      for (int c0 = 0; c0 < nw; c0 += 16) {
-        uint32_t v[16];
-        tc::ld16(lane_base + buf * NT + c0, v);
+      const int cw = nw >> 1;                      // columns per warpgroup (multiple of 32)
+      const int c_lo = h * cw;
+      const bool all_real = (nt * NT + nw) <= d.Cout;   // no padded output channels in this tile
+      for (int c0 = c_lo; c0 < c_lo + cw; c0 += 32) {
+        uint32_t v0[16], v1[16];
+        tc::ld16(lane_base + buf * NT + c0, v0);
+        tc::ld16(lane_base + buf * NT + c0 + 16, v1);
         tc::wait_ld();
-        if (c0 + 16 >= nw) {   // all columns of this buffer are in registers: release it
+        if (c0 + 32 >= c_lo + cw) {   // this warp's columns are all in registers: release the buffer
           tc::fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&d_empty[buf]);
         }
         if (valid) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int co = nt * NT + c0 + i;
-            if (co < d.Cout) {
-              float y = fmaf(__uint_as_float(v[i]), d.inv, shift ? __ldg(shift + co) : 0.f);
+          const int cg = nt * NT + c0;
+          float* o = out + (static_cast<size_t>(b) * d.Cout + cg) * d.P + p;
+          auto emit = [&](uint32_t raw, int i) {
+            const int co = cg + i;
+            if (all_real || co < d.Cout) {
+              float y = fmaf(__uint_as_float(raw), d.inv, shift ? __ldg(shift + co) : 0.f);
               if (arow) y += __ldg(arow + static_cast<size_t>(co) * d.G);
-              orow[static_cast<size_t>(co) * d.P] = d.relu ? fmaxf(y, 0.f) : y;
+              o[static_cast<size_t>(i) * d.P] = fmaxf(y, floor_v);
             }
-          }
+          };
+#pragma unroll
+          for (int i = 0; i < 16; ++i) emit(v0[i], i);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) emit(v1[i], 16 + i);
         }
       }
+      if (warp == 4 && it < 4) PW_TL(3, 2 * it + 1);
     }
   }
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 2) tc::tmem_dealloc(tm, 512);
+  if (dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) dbg[126] = clock64();
+#undef PW_TL
 }
 
 }  // namespace sonet
@@ -307,11 +356,11 @@ extern "C" int sonet_pointwise_tc_pack(const float* W, int Cout, int Cin, void* 
   return SONET_OK;
 }
 
-extern "C" int sonet_pointwise_tc_forward(const float* x0, int C0, const float* x1, int C1, int B,
+static int launch_pointwise_tc(const float* x0, int C0, const float* x1, int C1, int B,
                                           int P, const void* blob, float inv_scale,
                                           const float* shift, int Cout, int relu,
                                           const float* addend, const int32_t* gidx, int G,
-                                          float* out, sonet_stream_t stream) {
+                                          float* out, long long* dbg, sonet_stream_t stream) {
   using namespace sonet;
   using namespace sonet::pwt;
   SONET_REQUIRE(B >= 0 && P >= 0 && C0 >= 1 && C1 >= 0 && Cout >= 1, "pointwise_tc: bad dimension");
@@ -333,6 +382,23 @@ extern "C" int sonet_pointwise_tc_forward(const float* x0, int C0, const float* 
   cudaFuncSetAttribute(pointwise_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   const int grid = static_cast<int>(std::min<long long>(items, sm_count()));
   pointwise_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, as_stream(stream)>>>(
-      x0, x1, static_cast<const unsigned char*>(blob), shift, addend, gidx, out, d);
+      x0, x1, static_cast<const unsigned char*>(blob), shift, addend, gidx, out, d, dbg);
   return check_launch("pointwise_tc");
+}
+
+extern "C" int sonet_pointwise_tc_forward(const float* x0, int C0, const float* x1, int C1, int B,
+                                          int P, const void* blob, float inv_scale,
+                                          const float* shift, int Cout, int relu,
+                                          const float* addend, const int32_t* gidx, int G,
+                                          float* out, sonet_stream_t stream) {
+  return launch_pointwise_tc(x0, C0, x1, C1, B, P, blob, inv_scale, shift, Cout, relu, addend, gidx, G,
+                             out, nullptr, stream);
+}
+
+extern "C" int sonet_debug_pointwise_tc_timeline(const float* x0, int C0, int B, int P,
+                                                 const void* blob, float inv_scale, int Cout,
+                                                 float* out, long long* timeline128,
+                                                 sonet_stream_t stream) {
+  return launch_pointwise_tc(x0, C0, nullptr, 0, B, P, blob, inv_scale, nullptr, Cout, 1, nullptr,
+                             nullptr, 0, out, timeline128, stream);
 }

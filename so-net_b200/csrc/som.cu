@@ -28,7 +28,7 @@ template <int KK>
 __global__ void __launch_bounds__(256)
     som_assign_kernel(const float* __restrict__ x, const float* __restrict__ node, int N, int M,
                       int32_t* __restrict__ idx32, int64_t* __restrict__ idx64,
-                      int32_t* __restrict__ row_flag) {
+                      int32_t* __restrict__ row_flag, int32_t* __restrict__ mask) {
   __shared__ float4 snode[SOM_MAX_M];
   const int b = blockIdx.y;
   const float* nb = node + static_cast<size_t>(b) * 3 * M;
@@ -37,9 +37,11 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
 
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+  const bool live = n < N;
+  if (!live && mask == nullptr) return;   // (with a fused mask the whole warp stays for the shuffles)
   const float* xb = x + static_cast<size_t>(b) * 3 * N;
-  const float px = xb[n], py = xb[N + n], pz = xb[2 * N + n];
+  const int nl = live ? n : 0;
+  const float px = xb[nl], py = xb[N + nl], pz = xb[2 * N + nl];
 
   float bd[KK];
   int bi[KK];
@@ -70,6 +72,30 @@ __global__ void __launch_bounds__(256)
       }
     }
   }
+  if (mask != nullptr) {
+    // Fused dense one-hot mask (util/som.py:255-265), M % 32 == 0: the warp writes the KK rows of
+    // each of its 32 points cooperatively — every lane M/32 consecutive ints of a row, so a row
+    // (M*4 bytes) is one coalesced store instruction; the index comes from the owning lane by
+    // shuffle. 4 B/point read, 4*M*KK B/point written: pure HBM streaming.
+    const int lane = threadIdx.x & 31;
+    const int per = M >> 5;                       // ints per lane and row (2 for M = 64)
+    const int n_base = n - lane;                  // first point of this warp
+    const size_t mrow0 = static_cast<size_t>(b) * KK * N;
+    for (int r = 0; r < 32; ++r) {
+      if (n_base + r >= N) break;                 // warp-uniform
+#pragma unroll
+      for (int s = 0; s < KK; ++s) {
+        const int id = __shfl_sync(0xffffffffu, bi[s], r);
+        int32_t* dst = mask + (mrow0 + static_cast<size_t>(s) * N + n_base + r) * M + lane * per;
+        if (per == 2) {
+          __stcs(reinterpret_cast<int2*>(dst), make_int2(id == 2 * lane, id == 2 * lane + 1));
+        } else {
+          for (int e = 0; e < per; ++e) dst[e] = (id == lane * per + e) ? 1 : 0;
+        }
+      }
+    }
+  }
+  if (!live) return;
   const size_t o = static_cast<size_t>(b) * KK * N + n;
 #pragma unroll
   for (int s = 0; s < KK; ++s) {
@@ -212,9 +238,10 @@ __global__ void __launch_bounds__(256)
 
 }  // namespace sonet
 
-extern "C" int sonet_som_assign(const float* x, const float* node, int B, int N, int M, int k,
-                                int32_t* min_idx_i32, int64_t* min_idx_i64, int32_t* count,
-                                int32_t* row_max, float* cluster_mean, sonet_stream_t stream) {
+static int som_assign_impl(const float* x, const float* node, int B, int N, int M, int k,
+                           int32_t* min_idx_i32, int64_t* min_idx_i64, int32_t* count,
+                           int32_t* row_max, float* cluster_mean, int32_t* fused_mask,
+                           sonet_stream_t stream) {
   using namespace sonet;
   SONET_REQUIRE(B >= 0 && N >= 0, "som_assign: negative dimension");
   SONET_REQUIRE(M >= 1 && M <= SOM_MAX_M, "som_assign: M=%d out of range [1,%d]", M, SOM_MAX_M);
@@ -231,10 +258,10 @@ extern "C" int sonet_som_assign(const float* x, const float* node, int B, int N,
   if (N > 0) {
     dim3 grid((N + 255) / 256, B);
     switch (k) {
-      case 1: som_assign_kernel<1><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64, row_flag); break;
-      case 2: som_assign_kernel<2><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64, row_flag); break;
-      case 3: som_assign_kernel<3><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64, row_flag); break;
-      default: som_assign_kernel<4><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64, row_flag); break;
+      case 1: som_assign_kernel<1><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64, row_flag, fused_mask); break;
+      case 2: som_assign_kernel<2><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64, row_flag, fused_mask); break;
+      case 3: som_assign_kernel<3><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64, row_flag, fused_mask); break;
+      default: som_assign_kernel<4><<<grid, 256, 0, st>>>(x, node, N, M, min_idx_i32, min_idx_i64, row_flag, fused_mask); break;
     }
     int rc = check_launch("som_assign");
     if (rc) return rc;
@@ -245,6 +272,27 @@ extern "C" int sonet_som_assign(const float* x, const float* node, int B, int N,
     return check_launch("som_stats");
   }
   return SONET_OK;
+}
+
+extern "C" int sonet_som_assign(const float* x, const float* node, int B, int N, int M, int k,
+                                int32_t* min_idx_i32, int64_t* min_idx_i64, int32_t* count,
+                                int32_t* row_max, float* cluster_mean, sonet_stream_t stream) {
+  return som_assign_impl(x, node, B, N, M, k, min_idx_i32, min_idx_i64, count, row_max, cluster_mean,
+                         nullptr, stream);
+}
+
+extern "C" int sonet_som_query_topk(const float* x, const float* node, int B, int N, int M, int k,
+                                    int32_t* mask, int32_t* row_max, int64_t* min_idx_i64,
+                                    int32_t* min_idx_i32, sonet_stream_t stream) {
+  using namespace sonet;
+  SONET_REQUIRE(mask && row_max && min_idx_i32, "som_query_topk: null pointer");
+  if (M % 32 != 0 || (M / 32 == 2 && (reinterpret_cast<uintptr_t>(mask) & 7u))) {
+    int rc = som_assign_impl(x, node, B, N, M, k, min_idx_i32, min_idx_i64, nullptr, row_max, nullptr,
+                             nullptr, stream);
+    return rc ? rc : sonet_som_mask(min_idx_i32, B, k * N, M, mask, stream);
+  }
+  return som_assign_impl(x, node, B, N, M, k, min_idx_i32, min_idx_i64, nullptr, row_max, nullptr,
+                         mask, stream);
 }
 
 extern "C" int sonet_som_mask(const int32_t* min_idx_i32, int B, int kN, int M, int32_t* mask,

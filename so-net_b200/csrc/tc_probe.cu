@@ -120,3 +120,56 @@ extern "C" int sonet_debug_tc_probe(const float* A, const float* Bm, int N, int 
                                                        swap_fields, D);
   return check_launch("tc_probe");
 }
+
+// ---- MMA rate microbenchmark: `iters` back-to-back M=128 x N x 16 MMAs, SS or TS mode -----------
+namespace sonet {
+__global__ void __launch_bounds__(128, 1)
+    tc_rate_kernel(int mode, int N, uint32_t sbo, int iters, long long* __restrict__ cycles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tc::tmem_alloc(&tmem_base_s, 512);
+    tc::tmem_relinquish();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tm = tmem_base_s;
+  if (warp == 1) {
+    const uint32_t idesc = tc::idesc_f16_f32(128, N);
+    const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem) + 16384;
+    const uint64_t ad = tc::smem_desc(a_addr, 128, sbo), bd = tc::smem_desc(b_addr, 128, sbo);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      if (mode == 0)
+        tc::mma_ss_elect(tm, ad + (i & 3) * 16, bd + (i & 3) * 16, idesc, 1);
+      else
+        tc::mma_ts_elect(tm, tm + 256 + (i & 3) * 8, bd + (i & 3) * 16, idesc, 1);
+    }
+    tc::commit_elect(&bar);
+    tc::mbar_wait_bounded(&bar, 0, 77);
+    const long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0) cycles[0] = t1 - t0;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tm, 512);
+}
+}  // namespace sonet
+
+extern "C" int sonet_debug_tc_mma_rate(int mode, int N, int sbo, int iters, long long* cycles,
+                                       sonet_stream_t stream) {
+  using namespace sonet;
+  SONET_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && cycles, "tc_mma_rate: bad args");
+  cudaFuncSetAttribute(tc_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  tc_rate_kernel<<<1, 128, 64 * 1024, as_stream(stream)>>>(mode, N, static_cast<uint32_t>(sbo), iters, cycles);
+  return check_launch("tc_mma_rate");
+}

@@ -22,6 +22,8 @@ _SIGNATURES = {
     "sonet_index_max_cpu_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int],
     "sonet_som_assign": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                          c_void_p, c_void_p, c_void_p, c_void_p],
+    "sonet_som_query_topk": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_void_p],
     "sonet_som_mask": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "sonet_som_decenter": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                            c_void_p, c_void_p, c_void_p],
@@ -60,6 +62,9 @@ _SIGNATURES = {
                                    c_int, c_void_p, c_void_p],
     "sonet_debug_pointresnet_tc_timeline": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                             c_void_p, c_void_p, c_void_p],
+    "sonet_debug_pointwise_tc_timeline": [c_void_p, c_int, c_int, c_int, c_void_p, ctypes.c_float,
+                                          c_int, c_void_p, c_void_p, c_void_p],
+    "sonet_debug_tc_mma_rate": [c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "sonet_debug_tc_probe": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                              c_void_p],
     "sonet_last_error_string": [],

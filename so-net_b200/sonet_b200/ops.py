@@ -372,3 +372,21 @@ def pointresnet_tc_pool(x_sorted, blob, fparams, node_sorted, pos0, M):
         _call("sonet_pool_finalize", _C.ptr(keys), _C.ptr(p0), B, 384, int(M), _C.ptr(out),
               _stream(x_sorted))
     return out
+
+
+def som_query_topk(x, node, k):
+    """BatchSOM.query_topk in one launch -> (mask [B,kN,M] i32, row_max [B,M] i32,
+    min_idx [B,kN] i64, min_idx_i32 [B,kN])."""
+    _chk(x, "x", torch.float32)
+    _chk(node, "node", torch.float32)
+    B, _, N = x.shape
+    M = node.shape[2]
+    dev = x.device
+    with torch.cuda.device(dev):
+        mask = torch.empty((B, k * N, M), dtype=torch.int32, device=dev)
+        row_max = torch.empty((B, M), dtype=torch.int32, device=dev)
+        idx64 = torch.empty((B, k * N), dtype=torch.int64, device=dev)
+        idx32 = torch.empty((B, k * N), dtype=torch.int32, device=dev)
+        _call("sonet_som_query_topk", _C.ptr(x), _C.ptr(node), B, N, M, int(k), _C.ptr(mask),
+              _C.ptr(row_max), _C.ptr(idx64), _C.ptr(idx32), _stream(x))
+    return mask, row_max, idx64, idx32

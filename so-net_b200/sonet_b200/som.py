@@ -32,11 +32,10 @@ class BatchSOM():
         node = self.node
         if node.shape[0] != x.shape[0]:
             node = node.expand(x.shape[0], node.shape[1], node.shape[2])
-        a = ops.som_assign(x.detach().contiguous(), node.contiguous(), k, want_i64=True,
-                           want_stats=False)
-        self.last_assignment = a
-        mask = ops.som_mask(a["min_idx_i32"], M)
-        return mask, a["row_max"], a["min_idx_i64"]
+        mask, row_max, idx64, idx32 = ops.som_query_topk(x.detach().contiguous(), node.contiguous(), k)
+        self.last_assignment = dict(min_idx_i32=idx32, min_idx_i64=idx64, row_max=row_max,
+                                    count=None, cluster_mean=None)
+        return mask, row_max, idx64
 
     def query(self, x):
         """k=1 variant (util/som.py:271-293): (mask [B,N,M] float, mask_row_max [B,M] float)."""
