@@ -289,9 +289,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    gathered = torch.empty(total_rows, CLASSES, dtype=torch.float32, device=dev) if world > 1 \
+        else None
+
     def gpu_step():
         model.test_model()
-        return sdist.all_gather_rows(model.score, total_rows)
+        return sdist.all_gather_rows(model.score, total_rows, out=gathered)
 
     # ---- (1) device-resident arm -------------------------------------------------------------------
     model.set_input(*host)
@@ -329,7 +332,7 @@ def main():
     def e2e_step():
         model.set_input(*host)                             # H2D (pinned, async on the stream)
         model.test_model()
-        scores = sdist.all_gather_rows(model.score, total_rows)
+        scores = sdist.all_gather_rows(model.score, total_rows, out=gathered)
         return scores.cpu()                                # D2H + sync
     for _ in range(args.warmup):
         e2e_step()
@@ -439,6 +442,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes * world},
                 "gpu_launches": launches, "wall_s_timed_region": round(wall, 4),
+                "step_ms": {"min": round(min(step_ms), 4), "median": round(statistics.median(step_ms), 4),
+                            "max": round(max(step_ms), 4)},
                 "clocks": clocks, "roofline": roofline, "kernels": kernels,
                 "standalone_kernels": standalone,
                 "cpu_baseline": cpu_baseline,

@@ -41,15 +41,17 @@ def shard_bounds(total, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def all_gather_rows(local, total_rows=None):
+def all_gather_rows(local, total_rows=None, out=None):
     """Gather [rows_r, ...] shards from every rank into [sum rows, ...] in rank order.
-    Equal shards use one all_gather_into_tensor; ragged shards pad to the largest."""
+    Equal shards use one all_gather_into_tensor (into `out` when given: a persistent buffer avoids
+    a caching-allocator round trip per step); ragged shards pad to the largest."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return local
     world = dist.get_world_size()
     local = local.contiguous()
     if total_rows is None or total_rows % world == 0:
-        out = local.new_empty((local.shape[0] * world,) + tuple(local.shape[1:]))
+        if out is None:
+            out = local.new_empty((local.shape[0] * world,) + tuple(local.shape[1:]))
         dist.all_gather_into_tensor(out, local)
         return out
     sizes = [shard_bounds(total_rows, r, world) for r in range(world)]

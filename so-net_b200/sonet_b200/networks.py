@@ -12,6 +12,7 @@ remain available as lazily materialised attributes for callers that read them
 (models/segmenter.py:90).
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -309,7 +310,12 @@ class Segmenter(nn.Module):
             o3 = o2 + n_node
             w_point = torch.cat((w[0:o0], w[o1:o2]), dim=0).contiguous()     # coords | first_pn_out
             w_node = torch.cat((w[o2:o3], w[o0:o1], w[o3:]), dim=0).contiguous()  # node|onehot|global
-            self._l1_pack = (w_point, w_node)
+            tc = None
+            if os.environ.get("SONET_TC", "1") != "0":      # tcgen05 images of both halves
+                bp, ip = ops.pointwise_tc_pack(w_point.t().contiguous())
+                bn, inn = ops.pointwise_tc_pack(w_node.t().contiguous())
+                tc = (bp.to(w.device), ip, bn.to(w.device), inn)
+            self._l1_pack = (w_point, w_node, tc)
             self._l1_key = key
         return self._l1_pack + (shift,)
 
@@ -336,15 +342,25 @@ class Segmenter(nn.Module):
         if use_sn:
             small.append(torch.cat((sn,) * k, dim=2))
         pt = torch.cat(small, dim=1).contiguous()                       # [B,12,kN]
-        w_point, w_node, shift = self._pack_layer1(pt.shape[1], 16, first_pn_out.shape[1],
-                                                   node_first.shape[1] + node_knn.shape[1]
-                                                   + node_final.shape[1])
+        w_point, w_node, tc, shift = self._pack_layer1(pt.shape[1], 16, first_pn_out.shape[1],
+                                                       node_first.shape[1] + node_knn.shape[1]
+                                                       + node_final.shape[1])
         cloud = torch.cat((self._onehot(label, B, x.device), feature), dim=1)   # [B,1040]
         node_in = torch.cat((node_first, node_knn, node_final,
                              cloud.unsqueeze(2).expand(B, cloud.shape[1], M)), dim=1).contiguous()
-        addend = ops.pointwise_layer(node_in, w_node, None, None, False)        # [B,1024,M]
-        out1 = ops.pointwise_layer(pt, w_point, None, shift, self.layer1.activation == 'relu',
-                                   x1=first_pn_out.contiguous(), addend=addend, gidx=min_idx_i32)
+        relu1 = self.layer1.activation == 'relu'
+        if tc is not None:
+            bp, ip, bn, inn = tc
+            cout = w_point.shape[1]
+            addend = ops.pointwise_layer_tc(node_in, bn, inn, None, cout, False)   # [B,1024,M]
+            out1 = ops.pointwise_layer_tc(pt, bp, ip, shift, cout, relu1,
+                                          x1=first_pn_out.contiguous(), addend=addend,
+                                          gidx=min_idx_i32)
+        else:
+            addend = ops.pointwise_layer(node_in, w_node, None, None, False)
+            out1 = ops.pointwise_layer(pt, w_point, None, shift, relu1,
+                                       x1=first_pn_out.contiguous(), addend=addend,
+                                       gidx=min_idx_i32)
         out = self.layer3(self.layer2(out1))
         return self._tail(out, k, N)
 

@@ -107,7 +107,8 @@ def test_segmenter_vs_reference_golden_and_dropin_signature(oracle_mod):
                          enc.first_pn_out, gat(enc.first_pn_out_masked_max),
                          gat(enc.knn_feature_1), gat(enc.final_pn_out), m.feature)
     assert_golden(g, "score_segmenter", s2)
-    assert_close(s2, m.score_segmenter, "forward vs forward_nodes", 2e-5)
+    # two numeric paths (dense fp32 concat GEMM vs split tcgen05 GEMMs): both inside the 1e-4 bar
+    assert_close(s2, m.score_segmenter, "forward vs forward_nodes")
 
 
 def test_autoencoder_vs_reference_golden():
@@ -172,3 +173,64 @@ def test_training_step_runs_on_gpu_and_changes_weights():
     assert not torch.equal(w0, m.encoder.first_pointnet.layers[0].conv.weight.detach())
     m.test_model()     # folded weights are re-packed after the in-place optimizer update
     assert torch.isfinite(m.score).all()
+
+
+def test_segmenter_cfg3_full_size(oracle_mod):
+    """BASELINE.json configs[2]: segmenter forward, B=32, N=1024. Full batch: shard invariance
+    (bit-exact halves) + finiteness; a 2-cloud slice against the oracle (1e-4)."""
+    from sonet_b200 import segmenter, synth
+    B, N = 32, 1024
+    opt = synth.make_opt("segmenter", batch_size=B, input_pc_num=N)
+    st = build_states("segmenter", opt, seed=41)
+    inp = synth.synth_inputs(B, N, seed=41)
+    m = segmenter.Model(_gpu_opt(opt))
+    m.encoder.load_state_dict(st["encoder"])
+    m.segmenter.load_state_dict(st["head"])
+    seg = torch.zeros(B, N, dtype=torch.int64)
+    keys = ("pc", "sn", "label")
+    m.set_input(inp["pc"], inp["sn"], inp["label"], seg, inp["node"], inp["node_knn_I"])
+    m.test_model()
+    full = m.score_segmenter.clone()
+    assert full.shape == (B, 50, N) and torch.isfinite(full).all()
+    halves = []
+    for lo in (0, 16):
+        sl = slice(lo, lo + 16)
+        m.set_input(inp["pc"][sl], inp["sn"][sl], inp["label"][sl], seg[sl], inp["node"][sl],
+                    inp["node_knn_I"][sl])
+        m.test_model()
+        halves.append(m.score_segmenter.clone())
+    assert torch.equal(full, torch.cat(halves))
+    cpu_opt = synth.make_opt("segmenter", batch_size=2, input_pc_num=N)
+    o = oracle_mod.encoder_forward(st["encoder"], cpu_opt, inp["pc"][:2], inp["sn"][:2],
+                                   inp["node"][:2], inp["node_knn_I"][:2])
+    want = oracle_mod.segmenter_forward(st["head"], cpu_opt, o, inp["pc"][:2], inp["sn"][:2],
+                                        inp["label"][:2])
+    assert_close(full[:2], want, "segmenter cfg-3 slice vs oracle")
+
+
+def test_autoencoder_cfg4_full_size(oracle_mod):
+    """BASELINE.json configs[3]: AE forward + Chamfer, B=32, N=5000: finite, deterministic,
+    shard-consistent per-cloud losses; Chamfer of a 2-cloud slice against the oracle."""
+    from sonet_b200 import autoencoder, synth
+    B, N = 32, 5000
+    opt = synth.make_opt("autoencoder", batch_size=B, input_pc_num=N)
+    st = build_states("autoencoder", opt, seed=43)
+    inp = synth.synth_inputs(B, N, seed=43)
+    m = autoencoder.Model(_gpu_opt(opt))
+    m.encoder.load_state_dict(st["encoder"])
+    m.decoder.load_state_dict(st["head"])
+    keys = ("pc", "sn", "label", "node", "node_knn_I")
+    m.set_input(*[inp[k] for k in keys])
+    m.test_model()
+    loss, arr = float(m.loss), m.chamfer_criteria.loss_array.clone()
+    pred = m.predicted_pc.clone()
+    assert pred.shape == (B, 3, 1280) and np.isfinite(loss) and arr.shape == (B,)
+    m.test_model()
+    assert float(m.loss) == loss and torch.equal(arr, m.chamfer_criteria.loss_array)
+    m.set_input(*[inp[k][:16] for k in keys])
+    m.test_model()
+    # per-cloud losses are shard-consistent; not bit-exact because the out-of-scope decoder is
+    # PyTorch/cuDNN, whose conv algorithm choice depends on the batch size
+    assert_close(m.chamfer_criteria.loss_array, arr[:16], "cfg-4 shard consistency", 1e-5)
+    o = oracle_mod.chamfer(pred[:2].cpu(), inp["pc"][:2])
+    assert_close(arr[:2], o["loss_array"], "cfg-4 chamfer loss_array slice vs oracle")
