@@ -10,7 +10,11 @@ per step inside the timed region. Rank 0 prints ONE JSON line.
   value     clouds/s with inputs resident in HBM (CUDA events per step, L2 flushed between steps,
             max over ranks)
   e2e       the same metric through the public API classifier.Model.set_input()/test_model() with
-            pinned HOST buffers: H2D of every input and D2H of the logits inside the timed region
+            pinned HOST buffers: every step copies its full inputs host->device and reads its
+            logits device->host inside the timed region (K steps = K H2D + K D2H). The loop is a
+            serving loop pipelined by call order only: set_input (async, double-buffered, copy
+            stream) + test_model + async D2H of step i+1 are issued before the host waits for the
+            logits of step i
   roofline  dominant kernel (by measured device time) vs MEASURED_PEAKS.json, measured live with
             CUDA events around every C-ABI call of instrumented steps; `kernels` lists all of them
   cpu_baseline   the oracle port of the reference's PyTorch-CPU path (oracle/oracle.py; the pool
@@ -249,6 +253,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sonet_b200", choices=["sonet_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager op calls instead of CUDA-graph replay")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -275,6 +280,8 @@ def main():
     model = classifier.Model(opt)
     model.encoder.load_state_dict(synth.synth_state_dict(networks.Encoder(cpu_opt), seed=1))
     model.classifier.load_state_dict(synth.synth_state_dict(networks.Classifier(cpu_opt), seed=2))
+    if not args.no_graph:
+        model.enable_cuda_graph(True)                      # one graph launch per step
     inp = synth.synth_inputs(B, NPTS, seed=rank)            # each rank: its own shard
     keys = ("pc", "sn", "label", "node", "node_knn_I")
     host = [inp[k].pin_memory() for k in keys]
@@ -329,21 +336,37 @@ def main():
     value = total_rows * args.steps / (total_ms * 1e-3)
 
     # ---- (2) end-to-end arm: host buffers through the public Model API ------------------------------
-    def e2e_step():
-        model.set_input(*host)                             # H2D (pinned, async on the stream)
-        model.test_model()
-        scores = sdist.all_gather_rows(model.score, total_rows, out=gathered)
-        return scores.cpu()                                # D2H + sync
-    for _ in range(args.warmup):
-        e2e_step()
+    # A serving loop over the public API, software-pipelined by call order only: the (async,
+    # double-buffered, copy-stream) set_input of batch i+1 is issued before the logits of batch i
+    # are read back. Every step still copies its full inputs host->device (from pinned memory) and
+    # reads its logits device->host inside the timed region; K steps = K H2D + K D2H.
+    gathered2 = torch.empty_like(gathered) if gathered is not None else None
+
+    pinned_out = [torch.empty(total_rows, CLASSES, dtype=torch.float32).pin_memory() for _ in range(2)]
+    out_ready = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_run(k_steps):
+        def launch(i):                    # H2D + forward (+ all-gather) + async D2H of step i
+            model.set_input(*host)
+            model.test_model()
+            o = sdist.all_gather_rows(model.score, total_rows, out=(gathered, gathered2)[i & 1])
+            pinned_out[i & 1].copy_(o, non_blocking=True)
+            out_ready[i & 1].record()
+        launch(0)
+        last = None
+        for i in range(k_steps):
+            if i + 1 < k_steps:
+                launch(i + 1)                              # keep the GPU fed
+            out_ready[i & 1].synchronize()                 # logits of step i are on the host
+            last = pinned_out[i & 1]
+        return last
+    e2e_run(args.warmup)
     barrier()
-    t_e2e = []
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        e2e_step()
-        t_e2e.append(time.perf_counter() - t0)
+    flush.zero_()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_run(args.steps)
+    t_e2e = [time.perf_counter() - t0]
     barrier()
     e2e_total = torch.tensor([sum(t_e2e)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -353,6 +376,7 @@ def main():
 
     # ---- (3) instrumented steps: per-kernel device time with CUDA events ---------------------------
     prof_steps = []
+    model.enable_cuda_graph(False)                         # per-kernel events need eager calls
     for _ in range(3):
         flush.zero_()
         ops.PROFILE = []
@@ -438,7 +462,9 @@ def main():
                 "config": {"workload": WORKLOAD, "global_batch": total_rows,
                            "parallelism": "dp%d batch-sharded, 1 all-gather of logits/step" % world,
                            "l2": "256 MB flush write between timed steps (outside event pairs)",
-                           "weights": "random (seeded), BN stats randomised"},
+                           "weights": "random (seeded), BN stats randomised",
+                           "launch": "eager" if args.no_graph else
+                                     "CUDA-graph replay of the step (classifier.Model.enable_cuda_graph)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes * world},
                 "gpu_launches": launches, "wall_s_timed_region": round(wall, 4),

@@ -252,6 +252,11 @@ int sonet_debug_pointwise_tc_timeline(const float* x0, int C0, int B, int P, con
  * shared memory (SS, no-swizzle K-major, 8-row-group stride `sbo`), 1 = A from tensor memory (TS). */
 int sonet_debug_tc_mma_rate(int mode, int N, int sbo, int iters, long long* cycles,
                             sonet_stream_t stream);
+int sonet_debug_pointresnet_tc_pool_timeline(const float* x_sorted, int Cin, int B, int P,
+                                             const void* blob, const float* fparams,
+                                             const int32_t* node_sorted, const int32_t* pos0, int M,
+                                             int32_t* pool_keys, float* p0, long long* timeline64,
+                                             sonet_stream_t stream);
 int sonet_debug_tc_probe(const float* A, const float* Bm, int N, int K, int mode, int layout,
                          int swap_fields, float* D, sonet_stream_t stream);
 

@@ -290,19 +290,21 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
     const float* sh2 = sh1 + C1;
     const float* sh3 = sh2 + C2;
     const float inv1 = sh3[C3], inv2 = sh3[C3 + 1], inv3 = sh3[C3 + 2];  // 1 / weight pre-scale
-    for (int t = 0; t < my_tiles; ++t) {
-      const int tile = blockIdx.x + t * gridDim.x;
-      const int b = tile / tiles_per_cloud;
-      const int j = (tile - b * tiles_per_cloud) * TILE + r;
-      const bool valid = (tile < num_tiles) && (j < P);
-      const uint32_t par = t & 1;
-
-      // ---- layer 0 on CUDA cores: 32 of the 64 channels per warpgroup ----
-      if (warp == 4) PM_TL(1, 0);
-      float x[6];
+    // Layer 0 of tile t+1 is software-pipelined into tile t: its 6 inputs are prefetched while the
+    // layer-3 MMAs run, and it is computed as soon as the LAST layer-3 chunk of tile t has been read
+    // out of TMEM (all MMAs reading act0 are then complete) — before that chunk's pooling/stores —
+    // so the MMA warp can start tile t+1 about 2.3k cycles earlier (timeline, profiles/r01_summary.md).
+    float xn[6];
+    auto prefetch_x = [&](int tn) {
+      const int tile_n = blockIdx.x + tn * gridDim.x;
+      const int bn = tile_n / tiles_per_cloud;
+      const int jn = (tile_n - bn * tiles_per_cloud) * TILE + r;
+      const bool vn = (tile_n < num_tiles) && (jn < P);
 #pragma unroll
       for (int c = 0; c < 6; ++c)
-        x[c] = (valid && c < Cin) ? __ldg(x_in + (static_cast<size_t>(b) * Cin + c) * P + j) : 0.f;
+        xn[c] = (vn && c < Cin) ? __ldg(x_in + (static_cast<size_t>(bn) * Cin + c) * P + jn) : 0.f;
+    };
+    auto layer0 = [&]() {   // CUDA cores: 32 of the 64 channels per warpgroup, from xn[]
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         const int ch0 = 32 * h + 16 * g;
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
           const float* w = W0 + (ch0 + i) * 6;
           float a = sh0[ch0 + i];
 #pragma unroll
-          for (int c = 0; c < 6; ++c) a = fmaf(w[c], x[c], a);
+          for (int c = 0; c < 6; ++c) a = fmaf(w[c], xn[c], a);
           y[i] = fminf(fmaxf(a, 0.f), 65504.f);
         }
         uint32_t wds[16];
@@ -323,6 +325,17 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(b_act0);
+    };
+    if (my_tiles > 0) {
+      prefetch_x(0);
+      layer0();
+    }
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = blockIdx.x + t * gridDim.x;
+      const int b = tile / tiles_per_cloud;
+      const int j = (tile - b * tiles_per_cloud) * TILE + r;
+      const bool valid = (tile < num_tiles) && (j < P);
+      const uint32_t par = t & 1;
       if (warp == 4) PM_TL(1, 1);
 
       // ---- layer 1 epilogue: 64 of 128 channels, in place ----
@@ -370,6 +383,7 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(b_act2);
       if (warp == 4) PM_TL(1, 5);
+      if (t + 1 < my_tiles) prefetch_x(t + 1);   // in flight during the layer-3 MMAs
 
       // ---- layer 3 epilogue: four chunks of 96 channels, 48 per warpgroup; bare layer (no ReLU) ----
       float* orow = POOL ? nullptr : out + (static_cast<size_t>(b) * C3) * P + j;
@@ -418,6 +432,10 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&d3empty[buf]);
+        if (nc == L3_CHUNKS - 1 && t + 1 < my_tiles) {
+          if (warp == 4) PM_TL(1, 0);
+          layer0();                                // next tile's layer 0 first, then this chunk's work
+        }
         if (POOL) {
           const int co0 = L3_N * nc + 48 * h;
           // value -> order-preserving int key; lanes outside `in` contribute the identity
@@ -426,34 +444,72 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
             const int bits = __float_as_int(val);
             return bits ^ ((bits >> 31) & 0x7fffffff);
           };
-          // The 16 per-channel maxima of a group end up lane-distributed (lane i holds channel i;
-          // lanes 16+i the second node's) through selects, then ONE warp-wide red covers them: no
-          // per-channel divergent region (measured: per-channel `if (leader) atomicMax` costs
-          // ~100 cycles each in BSSY/BSYNC reconvergence).
+          // Per-node max of 16 channels over the warp's 32 rows as a shuffle transpose-reduce:
+          // recursive halving (xor 16, 8, 4, 2, then 1) leaves the max of channel
+          // c(lane) = lane bits 4..1 (bit 4 = MSB) in every lane pair after 16 shuffles — one
+          // per channel — and the even lanes issue ONE 16-lane red. (48 redux.sync per chunk
+          // serialise on two uniform registers: measured 4.7-5.8k cycles per chunk, longer than the
+          // chunk's MMAs, and the busy epilogue warps starved the MMA warp of issue slots.)
+          auto tmax16 = [&](const int (&k16)[16]) {
+            int a8[8], b4[4], c2[2];
+            {
+              const bool hi = (lane & 16) != 0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int keep = hi ? k16[8 + i] : k16[i], send = hi ? k16[i] : k16[8 + i];
+                a8[i] = max(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+              }
+            }
+            {
+              const bool hi = (lane & 8) != 0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int keep = hi ? a8[4 + i] : a8[i], send = hi ? a8[i] : a8[4 + i];
+                b4[i] = max(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+              }
+            }
+            {
+              const bool hi = (lane & 4) != 0;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const int keep = hi ? b4[2 + i] : b4[i], send = hi ? b4[i] : b4[2 + i];
+                c2[i] = max(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+              }
+            }
+            const bool hi = (lane & 2) != 0;
+            const int keep = hi ? c2[1] : c2[0], send = hi ? c2[0] : c2[1];
+            const int d1 = max(keep, __shfl_xor_sync(0xffffffffu, send, 2));
+            return max(d1, __shfl_xor_sync(0xffffffffu, d1, 1));
+          };
+          const int my_chan = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
+                              ((lane >> 1) & 1);
           auto pool_group = [&](const uint32_t (&v)[16], int cbase) {
-            float vals[16];
             if (pmode == 0 || pmode == 1) {
-              int mine = POOL_KEY_MIN;
+              int keys[16], ka[16];
+              float vals;
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const int key = keyof(v[i], cbase + i, vals[i]);
-                const int ma = __reduce_max_sync(0xffffffffu, inA ? key : POOL_KEY_MIN);
-                mine = (lane == i) ? ma : mine;
-                if (pmode == 1) {      // warp-uniform: a node boundary inside the warp
-                  const int mb = __reduce_max_sync(0xffffffffu, inB ? key : POOL_KEY_MIN);
-                  mine = (lane == 16 + i) ? mb : mine;
-                }
+                keys[i] = keyof(v[i], cbase + i, vals);
+                ka[i] = inA ? keys[i] : POOL_KEY_MIN;
               }
-              const bool second = lane >= 16;
-              if (!second || pmode == 1) {
-                int32_t* dst = (second ? krowB : krowA) +
-                               static_cast<size_t>(cbase + (lane & 15)) * pool.M;
+              int mine = tmax16(ka);
+              if (pmode == 1) {        // warp-uniform and rare: a node boundary inside the warp
+                int kb[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) kb[i] = inB ? keys[i] : POOL_KEY_MIN;
+                const int mb = tmax16(kb);
+                mine = (lane & 1) ? mb : mine;     // odd lanes carry the second node's maxima
+              }
+              if (!(lane & 1) || pmode == 1) {
+                int32_t* dst = ((lane & 1) ? krowB : krowA) +
+                               static_cast<size_t>(cbase + my_chan) * pool.M;
                 atomicMax(dst, mine);
               }
             } else if (pmode == 2) {   // three or more nodes in one warp (tiny nodes): per lane
+              float vals;
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const int key = keyof(v[i], cbase + i, vals[i]);
+                const int key = keyof(v[i], cbase + i, vals);
                 if (nd >= 0) atomicMax(krow + static_cast<size_t>(cbase + i) * pool.M, key);
               }
             }
@@ -636,6 +692,17 @@ extern "C" int sonet_pointresnet_tc_pool_forward(const float* x_sorted, int Cin,
                                                  sonet_stream_t stream) {
   sonet::PoolArgs pa{node_sorted, pos0, pool_keys, p0, M};
   return launch_pointresnet_tc(x_sorted, Cin, B, P, blob, fparams, nullptr, nullptr, &pa, stream);
+}
+
+extern "C" int sonet_debug_pointresnet_tc_pool_timeline(const float* x_sorted, int Cin, int B, int P,
+                                                        const void* blob, const float* fparams,
+                                                        const int32_t* node_sorted,
+                                                        const int32_t* pos0, int M,
+                                                        int32_t* pool_keys, float* p0,
+                                                        long long* timeline64,
+                                                        sonet_stream_t stream) {
+  sonet::PoolArgs pa{node_sorted, pos0, pool_keys, p0, M};
+  return launch_pointresnet_tc(x_sorted, Cin, B, P, blob, fparams, nullptr, timeline64, &pa, stream);
 }
 
 extern "C" int sonet_debug_pointresnet_tc_timeline(const float* x, int Cin, int B, int P,

@@ -65,6 +65,9 @@ _SIGNATURES = {
     "sonet_debug_pointwise_tc_timeline": [c_void_p, c_int, c_int, c_int, c_void_p, ctypes.c_float,
                                           c_int, c_void_p, c_void_p, c_void_p],
     "sonet_debug_tc_mma_rate": [c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sonet_debug_pointresnet_tc_pool_timeline": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                                 c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                                 c_void_p, c_void_p],
     "sonet_debug_tc_probe": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                              c_void_p],
     "sonet_last_error_string": [],

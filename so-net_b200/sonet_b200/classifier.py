@@ -1,52 +1,148 @@
 """classifier.Model — the caller-facing wrapper of models/classifier.py:15-153 (set_input /
 forward / test_model / optimize), built on the B200 networks. This is the public API bench.py
 times end to end: host tensors in through set_input, scores out.
+
+set_input is double-buffered and asynchronous: it copies into the input buffer set that the
+in-flight forward is NOT reading, on a dedicated copy stream, and forward() makes the compute
+stream wait for exactly that copy. The reference call order (set_input, then forward/test_model)
+is unchanged; a serving loop that wants the host-to-device copy hidden simply issues
+set_input(batch i+1) before it reads the scores of batch i.
 """
 import torch
 import torch.nn as nn
 
-from . import networks
+from . import networks, ops
+
+
+class _InputSet:
+    def __init__(self, B, N, M, som_k, dev):
+        self.pc = torch.empty(B, 3, N, dtype=torch.float32, device=dev)
+        self.sn = torch.empty(B, 3, N, dtype=torch.float32, device=dev)
+        self.label = torch.ones(B, dtype=torch.int64, device=dev)
+        self.node = torch.empty(B, 3, M, dtype=torch.float32, device=dev)
+        self.node_knn_I = torch.zeros(B, M, max(som_k, 1), dtype=torch.int64, device=dev)
+        self.ready = torch.cuda.Event() if dev.type == "cuda" else None      # copy finished
+        self.consumed = torch.cuda.Event() if dev.type == "cuda" else None   # last forward finished
 
 
 class Model():
     def __init__(self, opt):
         self.opt = opt
-        dev = opt.device
+        dev = opt.device if isinstance(opt.device, torch.device) else torch.device(opt.device)
         self.encoder = networks.Encoder(opt).to(dev)
         self.classifier = networks.Classifier(opt).to(dev)
         self.softmax_criteria = nn.CrossEntropyLoss().to(dev)
         self._optim = None
-
+        self._dev = dev
         B, N, M = opt.batch_size, opt.input_pc_num, opt.node_num
-        self.input_pc = torch.empty(B, 3, N, dtype=torch.float32, device=dev)
-        self.input_sn = torch.empty(B, 3, N, dtype=torch.float32, device=dev)
-        self.input_label = torch.ones(B, dtype=torch.int64, device=dev)
-        self.input_node = torch.empty(B, 3, M, dtype=torch.float32, device=dev)
-        self.input_node_knn_I = torch.zeros(B, M, opt.som_k, dtype=torch.int64, device=dev)
+        self._sets = [_InputSet(B, N, M, opt.som_k, dev) for _ in range(2)]
+        self._cur = 0
+        self._copy_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self._bind(self._sets[0])
         self.test_loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.test_accuracy = torch.zeros(1, dtype=torch.float32)
+        self._use_graph = False
+        self._graphs = {}
+
+    # ---- CUDA-graph replay of the eval forward ---------------------------------------------------
+    def enable_cuda_graph(self, flag=True):
+        """Replay test_model() as one CUDA graph per input buffer set (every C-ABI entry is
+        capturable: no allocation, no synchronisation). ~16 Python/ctypes op calls per step become
+        one graph launch, which is what bounds the end-to-end rate at this step time. Outputs
+        (score, feature, loss, encoder attributes) then live in per-graph static buffers that the
+        next replay of the same buffer set overwrites; graphs are re-captured when an input shape or
+        any parameter/buffer version changes."""
+        self._use_graph = bool(flag) and self._dev.type == "cuda"
+        self._graphs = {}
+
+    def _state_key(self, s):
+        if not hasattr(self, "_state_tensors"):
+            self._state_tensors = [t for m in (self.encoder, self.classifier)
+                                   for t in list(m.parameters()) + list(m.buffers())]
+        ver = 0
+        for t in self._state_tensors:
+            ver += t._version
+        return (tuple(s.pc.shape), tuple(s.node.shape), tuple(s.node_knn_I.shape), ver,
+                self.encoder.fuse_pool)
+
+    def _eval_forward(self):
+        self.feature = self.encoder(self.pc, self.sn, self.input_node, self.input_node_knn_I,
+                                    False, None)
+        self.score = self.classifier(self.feature, None)
+        self.loss = self.softmax_criteria(self.score, self.label)
+
+    def _test_model_graph(self):
+        s = self._sets[self._cur]
+        cur = torch.cuda.current_stream(self._dev)
+        cur.wait_event(s.ready)
+        key = self._state_key(s)
+        g = self._graphs.get(self._cur)
+        with torch.no_grad():
+            if g is None or g["key"] != key:
+                for _ in range(2):               # warm every host-side cache (folded/packed weights)
+                    self._eval_forward()
+                torch.cuda.synchronize(self._dev)
+                graph = torch.cuda.CUDAGraph()
+                k0, c0 = ops.KERNEL_LAUNCHES, ops.LAUNCHES
+                with torch.cuda.graph(graph):
+                    self._eval_forward()
+                g = dict(key=key, graph=graph, kernels=ops.KERNEL_LAUNCHES - k0,
+                         calls=ops.LAUNCHES - c0, feature=self.feature, score=self.score,
+                         loss=self.loss)
+                self._graphs[self._cur] = g
+            g["graph"].replay()
+        ops.KERNEL_LAUNCHES += g["kernels"]      # the replay launches the captured kernels
+        ops.LAUNCHES += g["calls"]
+        self.feature, self.score, self.loss = g["feature"], g["score"], g["loss"]
+        s.consumed.record(cur)
+
+    def _bind(self, s):
+        self.input_pc, self.input_sn, self.input_label = s.pc, s.sn, s.label
+        self.input_node, self.input_node_knn_I = s.node, s.node_knn_I
+        self.pc, self.sn, self.label = s.pc.detach(), s.sn.detach(), s.label.detach()
 
     def set_input(self, input_pc, input_sn, input_label, input_node, input_node_knn_I):
-        """Copy one batch (host or device tensors) into the pre-allocated device buffers
-        (models/classifier.py:64-72); pinned host tensors are copied asynchronously."""
-        self.input_pc.resize_(input_pc.size()).copy_(input_pc, non_blocking=True)
-        self.input_sn.resize_(input_sn.size()).copy_(input_sn, non_blocking=True)
-        self.input_label.resize_(input_label.size()).copy_(input_label, non_blocking=True)
-        self.input_node.resize_(input_node.size()).copy_(input_node, non_blocking=True)
-        self.input_node_knn_I.resize_(input_node_knn_I.size()).copy_(input_node_knn_I,
-                                                                     non_blocking=True)
-        self.pc = self.input_pc.detach()
-        self.sn = self.input_sn.detach()
-        self.label = self.input_label.detach()
+        """Copy one batch (host or device tensors) into the idle device buffer set
+        (models/classifier.py:64-72). Pinned host tensors are copied asynchronously on the copy
+        stream; the next forward waits for this copy only."""
+        self._cur ^= 1
+        s = self._sets[self._cur]
+        srcs = (input_pc, input_sn, input_label, input_node, input_node_knn_I)
+        dsts = (s.pc, s.sn, s.label, s.node, s.node_knn_I)
+        if self._copy_stream is None:
+            for d, t in zip(dsts, srcs):
+                d.resize_(t.size()).copy_(t)
+        else:
+            cur = torch.cuda.current_stream(self._dev)
+            cs = self._copy_stream
+            cs.wait_event(s.consumed)        # the forward that last read this set is done
+            if any(t.is_cuda for t in srcs):
+                cs.wait_stream(cur)          # device-side sources produced on the caller's stream
+            with torch.cuda.stream(cs):
+                for d, t in zip(dsts, srcs):
+                    if d.size() != t.size():
+                        d.resize_(t.size())
+                    d.copy_(t, non_blocking=True)
+                    if t.is_cuda:
+                        t.record_stream(cs)
+                s.ready.record(cs)
+        self._bind(s)
 
     def forward(self, is_train=False, epoch=None):
+        s = self._sets[self._cur]
+        if s.ready is not None:
+            torch.cuda.current_stream(self._dev).wait_event(s.ready)
         self.feature = self.encoder(self.pc, self.sn, self.input_node, self.input_node_knn_I,
                                     is_train, epoch)
         self.score = self.classifier(self.feature, epoch)
+        if s.consumed is not None:
+            s.consumed.record(torch.cuda.current_stream(self._dev))
 
     def test_model(self):
         self.encoder.eval()
         self.classifier.eval()
+        if self._use_graph:
+            return self._test_model_graph()
         with torch.no_grad():
             self.forward(is_train=False)
             self.loss = self.softmax_criteria(self.score, self.label)

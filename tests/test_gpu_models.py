@@ -234,3 +234,32 @@ def test_autoencoder_cfg4_full_size(oracle_mod):
     assert_close(m.chamfer_criteria.loss_array, arr[:16], "cfg-4 shard consistency", 1e-5)
     o = oracle_mod.chamfer(pred[:2].cpu(), inp["pc"][:2])
     assert_close(arr[:2], o["loss_array"], "cfg-4 chamfer loss_array slice vs oracle")
+
+
+def test_cuda_graph_replay_matches_eager_and_tracks_changes():
+    """classifier.Model.enable_cuda_graph: bit-identical scores, per-buffer-set graphs, re-capture
+    after a weight update, launch accounting."""
+    from sonet_b200 import ops, synth
+    opt = synth.make_opt("classifier", batch_size=4, input_pc_num=1024)
+    st = build_states("classifier", opt, seed=51)
+    m = _classifier(opt, st)
+    a, b = synth.synth_inputs(4, 1024, seed=51), synth.synth_inputs(4, 1024, seed=52)
+    keys = ("pc", "sn", "label", "node", "node_knn_I")
+    want = []
+    for inp in (a, b):
+        m.set_input(*[inp[k] for k in keys])
+        m.test_model()
+        want.append(m.score.clone())
+    m.enable_cuda_graph(True)
+    for rep in range(3):                       # alternates the two input sets / graphs
+        for inp, w in zip((a, b), want):
+            m.set_input(*[inp[k] for k in keys])
+            k0 = ops.KERNEL_LAUNCHES
+            m.test_model()
+            assert ops.KERNEL_LAUNCHES - k0 >= 15
+            assert torch.equal(m.score, w), rep
+    with torch.no_grad():
+        m.classifier.fc3.linear.bias.add_(1.0)  # parameter version changes -> re-capture
+    m.set_input(*[a[k] for k in keys])
+    m.test_model()
+    assert torch.allclose(m.score, want[0] + 1.0, atol=1e-5)

@@ -19,10 +19,24 @@ with torch.no_grad():
     blob, fpar = net._tc_params()
     out = torch.empty(64, 384, 15000, device="cuda")
     tl = torch.zeros(64, dtype=torch.int64, device="cuda")
-    for _ in range(2):
-        _C.check(_C.lib().sonet_debug_pointresnet_tc_timeline(
-            x.data_ptr(), 6, 64, 15000, blob.data_ptr(), fpar.data_ptr(), out.data_ptr(),
-            tl.data_ptr(), None), "timeline")
+    if "--pool" in sys.argv:
+        from sonet_b200 import ops, synth as _s
+        inp = _s.synth_inputs(64, 5000, seed=0)
+        pc, sn, node = inp["pc"].cuda(), inp["sn"].cuda(), inp["node"].cuda()
+        a = ops.som_assign(pc, node, 3)
+        xs, ns, p0i = ops.som_sort_decenter(pc, sn, a["cluster_mean"], a["min_idx_i32"], a["count"], 3)
+        keys = torch.empty(64, 384, 64, dtype=torch.int32, device="cuda")
+        _C.check(_C.lib().sonet_pool_keys_init(keys.data_ptr(), keys.numel(), None), "init")
+        p0 = torch.empty(64, 384, device="cuda")
+        for _ in range(2):
+            _C.check(_C.lib().sonet_debug_pointresnet_tc_pool_timeline(
+                xs.data_ptr(), 6, 64, 15000, blob.data_ptr(), fpar.data_ptr(), ns.data_ptr(),
+                p0i.data_ptr(), 64, keys.data_ptr(), p0.data_ptr(), tl.data_ptr(), None), "timeline")
+    else:
+        for _ in range(2):
+            _C.check(_C.lib().sonet_debug_pointresnet_tc_timeline(
+                x.data_ptr(), 6, 64, 15000, blob.data_ptr(), fpar.data_ptr(), out.data_ptr(),
+                tl.data_ptr(), None), "timeline")
     torch.cuda.synchronize()
 t = tl.cpu().tolist()
 mma, epi = t[:32], t[32:]
