@@ -238,8 +238,9 @@ int sonet_pointwise_tc_forward(const float* x0, int C0, const float* x1, int C1,
  * K-major core-matrix arrangements is used; swap_fields exchanges the LBO/SBO descriptor fields.
  * Exists so that tests can pin the descriptor encodings the fused point-MLP kernel relies on. */
 /* Same as sonet_pointresnet_tc_forward, additionally writing clock64() stamps of the phase
- * boundaries of CTA 0's 4th tile into timeline64[64] (device): [0..31] MMA warp, [32..63] an
- * epilogue warp. Used by tools/tc_timeline.py to see where a tile's cycles go. */
+ * boundaries of CTA 0's tile number timeline64[125] (host-set) into timeline64[128] (device): [0..31] MMA warp, [32..63] an
+ * epilogue warp, [64..123] act0-ready time of every tile, [126] kernel start, [127] kernel end.
+ * Used by tools/tc_timeline.py to see where a tile's cycles go. */
 int sonet_debug_pointresnet_tc_timeline(const float* x, int Cin, int B, int P, const void* blob,
                                         const float* fparams, float* out, long long* timeline64,
                                         sonet_stream_t stream);

@@ -57,7 +57,7 @@ constexpr int BLOB_BYTES =
     W1_BYTES + L2_STAGES * L2_STAGE_BYTES + L3_CHUNKS * L3_KSTAGES * L3_STAGE_BYTES;  // 655360
 constexpr int NFP = C0 * 6 + C0 + C1 + C2 + C3 + 4;   // W0 | shift0..3 | 1/wscale1..3 (floats)
 constexpr int NUM_THREADS = 384;
-constexpr int NBAR = 2 * NSLOT + 5 + 4 + 1;
+constexpr int NBAR = 2 * NSLOT + 3 + 4 + 4 + 4 + 1;
 // shared memory carve-up
 constexpr int OFF_W1 = 0;
 constexpr int OFF_RING = OFF_W1 + W1_BYTES;
@@ -106,10 +106,12 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
                           const unsigned char* __restrict__ blob, const float* __restrict__ fparams,
                           float* __restrict__ out, long long* __restrict__ dbg, PoolArgs pool) {
   using namespace pm;
-  // optional timeline (debug entry point only): clock64 at phase boundaries of CTA 0's 4th tile
+  // optional timeline (debug entry point only): clock64 at phase boundaries of CTA 0's tile
+  // number dbg[125] (set by the host before the launch)
+  const int tl_tile = (dbg != nullptr) ? static_cast<int>(dbg[125]) : -1;
 #define PM_TL(role, idx)                                                          \
   do {                                                                            \
-    if (dbg != nullptr && blockIdx.x == 0 && t == 3 && lane == 0)                 \
+    if (dbg != nullptr && blockIdx.x == 0 && t == tl_tile && lane == 0)           \
       dbg[(role) * 32 + (idx)] = clock64();                                       \
   } while (0)
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -119,15 +121,19 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
   uint64_t* empty = bars + NSLOT;          // [NSLOT]  MMA -> TMA
   uint64_t* b_act0 = bars + 2 * NSLOT;     // epilogue -> MMA
   uint64_t* b_d1 = b_act0 + 1;             // MMA -> epilogue
-  uint64_t* b_act1 = b_act0 + 2;
-  uint64_t* b_d2 = b_act0 + 3;
-  uint64_t* b_act2 = b_act0 + 4;
-  uint64_t* d3full = b_act0 + 5;           // [2]
+  uint64_t* b_d2 = b_act0 + 2;
+  uint64_t* b_act1s = b_act0 + 3;          // [4] one per layer-2 K slab (32 act1 channels)
+  uint64_t* b_act2q = b_act1s + 4;         // [4] one per layer-3 K stage (64 act2 channels)
+  uint64_t* d3full = b_act2q + 4;          // [2]
   uint64_t* d3empty = d3full + 2;          // [2]
   uint64_t* w1_full = d3empty + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: tells ptxas it is warp-uniform, so the role branches below are
+  // convergent regions and the MMA warp's address arithmetic can live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  if (dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) dbg[64 + 62] = clock64();
   const int tiles_per_cloud = (P + TILE - 1) / TILE;
   const int num_tiles = B * tiles_per_cloud;
   // every CTA runs the same number of iterations (a cluster consumes the weight stream in
@@ -144,9 +150,11 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
     }
     mbar_init(b_act0, 8);
     mbar_init(b_d1, 1);
-    mbar_init(b_act1, 8);
     mbar_init(b_d2, 1);
-    mbar_init(b_act2, 8);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&b_act1s[i], 8);
+      mbar_init(&b_act2q[i], 8);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&d3full[i], 1);
       mbar_init(&d3empty[i], 8);
@@ -162,19 +170,27 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
   __syncthreads();
   if (CL > 1) tc::cluster_sync_all();   // peers' barriers are initialised before any multicast lands
   tc::fence_after_sync();
-  const uint32_t tm = *tmem_ptr;
+  // All 512 columns are allocated, so the allocation base is column 0 / lane 0 by construction;
+  // using the constant keeps every TMEM address an immediate (checked once here).
+  if (*tmem_ptr != 0u) __trap();
+  constexpr uint32_t tm = 0;
 
+  // Code-size discipline: every stage loop below is deliberately NOT unrolled and every large
+  // block (layer 0, the chunk epilogue) has exactly one call site. The first version of this kernel
+  // was ~9k hot SASS instructions (147 KB) and ncu attributed 22 % of its non-idle stall samples to
+  // instruction fetch (stall_no_inst); see profiles/r01_summary.md.
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       mbar_arrive_expect_tx(w1_full, W1_BYTES);
       bulk_g2s(smem + OFF_W1, blob, W1_BYTES, w1_full);
-      uint32_t q = 0;
+      uint32_t slot = 0, use_par = 1;     // parity of the `empty` phase that frees `slot` (first lap: free)
+#pragma unroll 1
       for (int t = 0; t < my_tiles; ++t) {
         uint32_t off = W1_BYTES;
-        for (int s = 0; s < STAGES_PER_TILE; ++s, ++q) {
-          const uint32_t slot = q % NSLOT, use = q / NSLOT;
-          if (use > 0) tc::mbar_wait_bounded(&empty[slot], (use - 1) & 1, 100 + s);
+#pragma unroll 1
+        for (int s = 0; s < STAGES_PER_TILE; ++s) {
+          if (t > 0 || s >= NSLOT) tc::mbar_wait_relaxed(&empty[slot], use_par, 100 + s);
           const uint32_t bytes = stage_bytes(s);
           mbar_arrive_expect_tx(&full[slot], bytes);   // all CL slices land on this barrier
           if (CL == 1) {
@@ -185,6 +201,10 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
                                    blob + off + cta_rank * slice, slice, &full[slot], CL_MASK);
           }
           off += bytes;
+          if (++slot == NSLOT) {
+            slot = 0;
+            use_par ^= 1;
+          }
         }
       }
     }
@@ -192,10 +212,22 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
     // ============ MMA issuer: the warp stays converged, elect.sync issues from one lane ============
     constexpr uint32_t ID1 = tc::idesc_f16_f32(TILE, C1), ID2 = tc::idesc_f16_f32(TILE, C2),
                        ID3 = tc::idesc_f16_f32(TILE, L3_N);
-    const uint32_t w1_addr = smem_u32(smem + OFF_W1);
-    const uint32_t ring_addr = smem_u32(smem + OFF_RING);
+    // addresses through the compiler-visible cvta (not inline asm): candidates for the uniform path
+    const uint32_t w1_addr = static_cast<uint32_t>(__cvta_generic_to_shared(smem + OFF_W1));
+    const uint32_t ring_addr = static_cast<uint32_t>(__cvta_generic_to_shared(smem + OFF_RING));
     tc::mbar_wait_bounded(w1_full, 0, 1);
-    uint32_t q = 0;
+    uint32_t slot = 0, full_par = 0;
+    auto next_slot = [&]() {
+      if (++slot == NSLOT) {
+        slot = 0;
+        full_par ^= 1;
+      }
+    };
+    auto release_slot = [&]() {
+      if (CL == 1) tc::commit_elect(&empty[slot]);
+      else tc::commit_multicast_elect(&empty[slot], CL_MASK);
+    };
+#pragma unroll 1
     for (int t = 0; t < my_tiles; ++t) {
       const uint32_t par = t & 1;
       // ---- layer 1: D1[128 x 128] = act0[128 x 64] * W1^T (one N=128 MMA per product) ----
@@ -206,45 +238,33 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
       }
       tc::fence_after_sync();
       PM_TL(0, 0);
-      {
-        const uint64_t dh0 = bdesc(w1_addr, 1024), dl0 = bdesc(w1_addr + W1_BYTES / 2, 1024);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint32_t a_hi = tm + COL_A0 + 16 * ks, a_lo = a_hi + 8;
-          const uint64_t dh = dh0 + ks * 16, dl = dl0 + ks * 16;   // +256 B per K step
-          tc::mma_ts_elect(tm + COL_D1, a_hi, dh, ID1, ks > 0);
-          tc::mma_ts_elect(tm + COL_D1, a_lo, dh, ID1, 1);
-          tc::mma_ts_elect(tm + COL_D1, a_hi, dl, ID1, 1);
-        }
-      }
+      if (dbg != nullptr && blockIdx.x == 0 && lane == 0 && t < 60) dbg[64 + t] = clock64();
+      tc::mma_ts_stage<4>(tm + COL_D1, tm + COL_A0, bdesc(w1_addr, 1024),
+                          bdesc(w1_addr + W1_BYTES / 2, 1024), ID1, 0);
       tc::commit_elect(b_d1);
       PM_TL(0, 1);
-      // ---- layer 2: D2[128 x 256] = act1[128 x 128] * W2^T: 4 streamed K slabs of 32, N=256 ----
-      tc::mbar_wait_bounded(b_act1, par, 5);
-      tc::fence_after_sync();
-      PM_TL(0, 2);
-#pragma unroll
-      for (int kc = 0; kc < L2_STAGES; ++kc, ++q) {
-        const uint32_t slot = q % NSLOT;
-        tc::mbar_wait_bounded(&full[slot], (q / NSLOT) & 1, 6);
+      // ---- layer 2: D2[128 x 256] = act1[128 x 128] * W2^T: 4 streamed K slabs of 32, N=256.
+      // Each slab starts as soon as ITS 32 act1 channels are converted (per-slab barriers), so
+      // the layer-1 epilogue overlaps the layer-2 MMAs ----
+#pragma unroll 1
+      for (int kc = 0; kc < L2_STAGES; ++kc) {
+        tc::mbar_wait_bounded(&b_act1s[kc], par, 5);
+        if (kc == 0) PM_TL(0, 2);
+        tc::mbar_wait_bounded(&full[slot], full_par, 6);
         tc::fence_after_sync();
         const uint32_t sb = ring_addr + slot * SLOT_BYTES;
-        const uint64_t dh0 = bdesc(sb, 512), dl0 = bdesc(sb + L2_STAGE_BYTES / 2, 512);
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint32_t a_hi = tm + COL_D1 + 16 * (kc * 2 + ks), a_lo = a_hi + 8;
-          const uint64_t dh = dh0 + ks * 16, dl = dl0 + ks * 16;
-          tc::mma_ts_elect(tm + COL_D2, a_hi, dh, ID2, (kc | ks) != 0);
-          tc::mma_ts_elect(tm + COL_D2, a_lo, dh, ID2, 1);
-          tc::mma_ts_elect(tm + COL_D2, a_hi, dl, ID2, 1);
-        }
-        if (CL == 1) tc::commit_elect(&empty[slot]);
-        else tc::commit_multicast_elect(&empty[slot], CL_MASK);
+        tc::mma_ts_stage<2>(tm + COL_D2, tm + COL_D1 + 32 * kc, bdesc(sb, 512),
+                            bdesc(sb + L2_STAGE_BYTES / 2, 512), ID2, kc != 0);
+        release_slot();
+        next_slot();
       }
       tc::commit_elect(b_d2);
       PM_TL(0, 3);
-      // ---- layer 3: D3[128 x 384] = cat(act0, act2)[128 x 320] * W3^T: 4 chunks of N=96 ----
-      tc::mbar_wait_bounded(b_act2, par, 7);
+      // ---- layer 3: D3[128 x 384] = cat(act0, act2)[128 x 320] * W3^T: 4 chunks of N=96.
+      // Chunk 0 starts when layer 2's MMAs are complete (its accumulator aliases act1): K stage 0
+      // reads act0, K stage s >= 1 waits for act2 quarter s-1 only (already complete for chunks
+      // 1-3, where the wait falls through), so the layer-2 epilogue overlaps chunk 0's MMAs ----
+      tc::mbar_wait_bounded(b_d2, par, 7);
       tc::fence_after_sync();
       PM_TL(0, 4);
 #pragma unroll 1
@@ -254,25 +274,18 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
         tc::fence_after_sync();
         const uint32_t d = tm + COL_D3 + L3_N * buf;
         PM_TL(0, 5 + 2 * nc);
-#pragma unroll
-        for (int kc = 0; kc < L3_KSTAGES; ++kc, ++q) {
-          const uint32_t slot = q % NSLOT;
-          tc::mbar_wait_bounded(&full[slot], (q / NSLOT) & 1, 10);
+#pragma unroll 1
+        for (int kc = 0; kc < L3_KSTAGES; ++kc) {
+          if (kc > 0) tc::mbar_wait_bounded(&b_act2q[kc - 1], par, 9);
+          tc::mbar_wait_bounded(&full[slot], full_par, 10);
           tc::fence_after_sync();
           const uint32_t sb = ring_addr + slot * SLOT_BYTES;
-          const uint64_t dh0 = bdesc(sb, 1024), dl0 = bdesc(sb + L3_STAGE_BYTES / 2, 1024);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const int kg = kc * 4 + ks;  // 16-channel K group: 0-3 act0, 4-19 act2
-            const uint32_t a_hi = tm + (kg < 4 ? COL_A0 + 16 * kg : COL_D2 + 16 * (kg - 4));
-            const uint32_t a_lo = a_hi + 8;
-            const uint64_t dh = dh0 + ks * 16, dl = dl0 + ks * 16;
-            tc::mma_ts_elect(d, a_hi, dh, ID3, kg > 0);
-            tc::mma_ts_elect(d, a_lo, dh, ID3, 1);
-            tc::mma_ts_elect(d, a_hi, dl, ID3, 1);
-          }
-          if (CL == 1) tc::commit_elect(&empty[slot]);
-          else tc::commit_multicast_elect(&empty[slot], CL_MASK);
+          // 16-channel K groups: stage 0 = act0 (4 groups), stages 1-4 = act2 quarters
+          const uint32_t a0 = tm + (kc == 0 ? COL_A0 : COL_D2 + 64 * (kc - 1));
+          tc::mma_ts_stage<4>(d, a0, bdesc(sb, 1024), bdesc(sb + L3_STAGE_BYTES / 2, 1024), ID3,
+                              kc != 0);
+          release_slot();
+          next_slot();
         }
         tc::commit_elect(&d3full[buf]);
         PM_TL(0, 6 + 2 * nc);
@@ -290,11 +303,9 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
     const float* sh2 = sh1 + C1;
     const float* sh3 = sh2 + C2;
     const float inv1 = sh3[C3], inv2 = sh3[C3 + 1], inv3 = sh3[C3 + 2];  // 1 / weight pre-scale
-    // Layer 0 of tile t+1 is software-pipelined into tile t: its 6 inputs are prefetched while the
-    // layer-3 MMAs run, and it is computed as soon as the LAST layer-3 chunk of tile t has been read
-    // out of TMEM (all MMAs reading act0 are then complete) — before that chunk's pooling/stores —
-    // so the MMA warp can start tile t+1 about 2.3k cycles earlier (timeline, profiles/r01_summary.md).
-    float xn[6];
+    constexpr unsigned FULL = 0xffffffffu;
+
+    float xn[6];                        // layer-0 inputs of the NEXT tile, prefetched
     auto prefetch_x = [&](int tn) {
       const int tile_n = blockIdx.x + tn * gridDim.x;
       const int bn = tile_n / tiles_per_cloud;
@@ -304,247 +315,249 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
       for (int c = 0; c < 6; ++c)
         xn[c] = (vn && c < Cin) ? __ldg(x_in + (static_cast<size_t>(bn) * Cin + c) * P + jn) : 0.f;
     };
-    auto layer0 = [&]() {   // CUDA cores: 32 of the 64 channels per warpgroup, from xn[]
+    // Max of 16 channels over the warp's 32 rows as a shuffle transpose-reduce: recursive halving
+    // (xor 16, 8, 4, 2, then 1) leaves the max of channel c(lane) = lane bits 4..1 (bit 4 = MSB) in
+    // every lane pair after 16 shuffles — one per channel. (48 redux.sync per chunk serialise on
+    // two uniform registers: measured 4.7-5.8k cycles per chunk.) It runs on the RAW accumulators:
+    // y = fmaf(raw, inv3 > 0, shift) is monotone, so max_rows(y) == fmaf(max_rows(raw), ...) bit
+    // for bit and the affine map + key conversion are paid once per lane, not once per element.
+    auto tmax16 = [&](const float (&k16)[16]) {
+      float a8[8], b4[4], c2[2];
+      {
+        const bool hi = (lane & 16) != 0;
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const int ch0 = 32 * h + 16 * g;
-        float y[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float* w = W0 + (ch0 + i) * 6;
-          float a = sh0[ch0 + i];
-#pragma unroll
-          for (int c = 0; c < 6; ++c) a = fmaf(w[c], xn[c], a);
-          y[i] = fminf(fmaxf(a, 0.f), 65504.f);
+        for (int i = 0; i < 8; ++i) {
+          const float keep = hi ? k16[8 + i] : k16[i], send = hi ? k16[i] : k16[8 + i];
+          a8[i] = fmaxf(keep, __shfl_xor_sync(FULL, send, 16));
         }
-        uint32_t wds[16];
-        tc::split16_f16(y, wds);
-        tc::st16(lane_base + COL_A0 + ch0, wds);
       }
-      tc::wait_st();
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(b_act0);
+      {
+        const bool hi = (lane & 8) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float keep = hi ? a8[4 + i] : a8[i], send = hi ? a8[i] : a8[4 + i];
+          b4[i] = fmaxf(keep, __shfl_xor_sync(FULL, send, 8));
+        }
+      }
+      {
+        const bool hi = (lane & 4) != 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float keep = hi ? b4[2 + i] : b4[i], send = hi ? b4[i] : b4[2 + i];
+          c2[i] = fmaxf(keep, __shfl_xor_sync(FULL, send, 4));
+        }
+      }
+      const bool hi = (lane & 2) != 0;
+      const float keep = hi ? c2[1] : c2[0], send = hi ? c2[0] : c2[1];
+      const float d1 = fmaxf(keep, __shfl_xor_sync(FULL, send, 2));
+      return fmaxf(d1, __shfl_xor_sync(FULL, d1, 1));
     };
-    if (my_tiles > 0) {
-      prefetch_x(0);
-      layer0();
-    }
-    for (int t = 0; t < my_tiles; ++t) {
+    const int my_chan = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
+                        ((lane >> 1) & 1);
+
+    // The tile whose layer-3 chunks are being finished (plain scalars: a struct went to local
+    // memory). During the first step of an iteration they still describe the PREVIOUS tile.
+    int cx_b = 0, cx_nd = -1;
+    unsigned cx_vmask = 0;              // lanes holding a real row
+    bool cx_valid = false, cx_is_p0 = false, cx_any_p0 = false;
+    float* cx_orow = nullptr;
+
+    // POOL: per-node max of 16 channels. Rows are node-sorted, so the lanes of a warp fall into
+    // 1 (87 % of warps on the bench input), 2 or rarely more runs of equal node id; one pass of
+    // the loop per run: masked transpose-reduce, then the even lanes issue ONE 16-lane RED.MAX.
+    // The trip count is warp-uniform by construction.
+    auto pool_group = [&](const uint32_t (&v)[16], int cbase) {
+      const int co = cbase + my_chan;             // the channel this lane pair ends up owning
+      int32_t* kb = pool.keys + (static_cast<size_t>(cx_b) * C3 + co) * pool.M;
+      const float shift = sh3[co];
+      unsigned rem = cx_vmask;
+#pragma unroll 1
+      while (rem != 0) {
+        const int node = __shfl_sync(FULL, cx_nd, __ffs(rem) - 1);
+        const bool in = (cx_nd == node);
+        const unsigned run = __ballot_sync(FULL, in);
+        float ka[16];
+        if (run == FULL) {                        // the whole warp is one node: nothing to mask
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ka[i] = __uint_as_float(v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ka[i] = in ? __uint_as_float(v[i]) : -INFINITY;
+        }
+        const int bits = __float_as_int(fmaf(tmax16(ka), inv3, shift));
+        const int key = bits ^ ((bits >> 31) & 0x7fffffff);   // order-preserving float -> int
+        if (!(lane & 1)) atomicMax(kb + node, key);
+        rem &= ~run;
+      }
+      if (cx_any_p0) {              // warp-uniform and rare: one warp per cloud and column half
+        if (cx_is_p0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            pool.p0[static_cast<size_t>(cx_b) * C3 + cbase + i] =
+                fmaf(__uint_as_float(v[i]), inv3, sh3[cbase + i]);
+        }
+      }
+    };
+    auto store_group = [&](const uint32_t (&v)[16], int cbase) {   // lane = point: coalesced
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        cx_orow[static_cast<size_t>(cbase + i) * P] = fmaf(__uint_as_float(v[i]), inv3, sh3[cbase + i]);
+    };
+
+    uint32_t v0[16], v1[16], v2[16];    // this warp's 48 accumulator columns of one chunk
+    bool parked = false;                // v0..v2 hold the previous tile's last chunk
+    if (my_tiles > 0) prefetch_x(0);
+    // Iteration t: layer 0 .. layer-2 epilogue of tile t, then the chunk steps. Step -1 finishes
+    // the chunk parked by tile t-1 (its pooling runs while chunk 0's MMAs execute), steps 0..3 read
+    // chunk nc out of TMEM, release the buffer and finish it at once — except the last chunk,
+    // which stays parked so that the next tile's layer 0 starts immediately. One extra iteration
+    // drains the last parked chunk.
+#pragma unroll 1
+    for (int t = 0; t <= my_tiles; ++t) {
+      const bool live = t < my_tiles;
       const int tile = blockIdx.x + t * gridDim.x;
       const int b = tile / tiles_per_cloud;
       const int j = (tile - b * tiles_per_cloud) * TILE + r;
-      const bool valid = (tile < num_tiles) && (j < P);
+      const bool valid = live && (tile < num_tiles) && (j < P);
       const uint32_t par = t & 1;
-      if (warp == 4) PM_TL(1, 1);
-
-      // ---- layer 1 epilogue: 64 of 128 channels, in place ----
-      tc::mbar_wait_bounded(b_d1, par, 20);
-      tc::fence_after_sync();
-      if (warp == 4) PM_TL(1, 2);
+      int nd_next = -1, p0row = -1;
+      if (live) {
+        if (warp == 4) PM_TL(1, 0);
+        // ---- layer 0 on CUDA cores: 32 of the 64 channels per warpgroup, from xn[] ----
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          const int ch0 = 32 * h + 16 * g;
+          float y[16];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int ch0 = 64 * h + 16 * g;
-        uint32_t v[16];
-        tc::ld16(lane_base + COL_D1 + ch0, v);
-        tc::wait_ld();
-        float y[16];
+          for (int i = 0; i < 16; ++i) {
+            const float* w = W0 + (ch0 + i) * 6;
+            float a = sh0[ch0 + i];
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          y[i] = fminf(fmaxf(fmaf(__uint_as_float(v[i]), inv1, sh1[ch0 + i]), 0.f), 65504.f);
-        tc::split16_f16(y, v);
-        tc::st16(lane_base + COL_D1 + ch0, v);
-      }
-      tc::wait_st();
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(b_act1);
-      if (warp == 4) PM_TL(1, 3);
-
-      // ---- layer 2 epilogue: 128 of 256 channels, in place ----
-      tc::mbar_wait_bounded(b_d2, par, 21);
-      tc::fence_after_sync();
-      if (warp == 4) PM_TL(1, 4);
-#pragma unroll 2
-      for (int g = 0; g < 8; ++g) {
-        const int ch0 = 128 * h + 16 * g;
-        uint32_t v[16];
-        tc::ld16(lane_base + COL_D2 + ch0, v);
-        tc::wait_ld();
-        float y[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          y[i] = fminf(fmaxf(fmaf(__uint_as_float(v[i]), inv2, sh2[ch0 + i]), 0.f), 65504.f);
-        tc::split16_f16(y, v);
-        tc::st16(lane_base + COL_D2 + ch0, v);
-      }
-      tc::wait_st();
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(b_act2);
-      if (warp == 4) PM_TL(1, 5);
-      if (t + 1 < my_tiles) prefetch_x(t + 1);   // in flight during the layer-3 MMAs
-
-      // ---- layer 3 epilogue: four chunks of 96 channels, 48 per warpgroup; bare layer (no ReLU) ----
-      float* orow = POOL ? nullptr : out + (static_cast<size_t>(b) * C3) * P + j;
-      // POOL: lanes sharing a node form a group (rows are node-sorted: 1-2 groups per warp)
-      // (full-mask redux + a warp-uniform mode: a redux over match_any masks makes nvcc emit a
-      // per-group uniformisation loop, measured 2x slower than not fusing at all)
-      constexpr int POOL_KEY_MIN = static_cast<int>(0x80000000u);
-      int nd = -1, pmode = -1, laneA = 0, laneB = 0;
-      bool inA = false, inB = false, is_p0 = false, any_p0 = false;
-      int32_t *krow = nullptr, *krowA = nullptr, *krowB = nullptr;
-      if (POOL) {
-        if (valid) nd = __ldg(pool.node_sorted + static_cast<size_t>(b) * P + j);
-        is_p0 = valid && (j == __ldg(pool.pos0 + b));
-        any_p0 = __any_sync(0xffffffffu, is_p0);
-        int32_t* kb = pool.keys + (static_cast<size_t>(b) * C3) * pool.M;
-        krow = kb + max(nd, 0);
-        const unsigned vmask = __ballot_sync(0xffffffffu, nd >= 0);
-        if (vmask != 0) {
-          laneA = __ffs(vmask) - 1;
-          const int nodeA = __shfl_sync(0xffffffffu, nd, laneA);
-          inA = (nd == nodeA);
-          krowA = kb + nodeA;
-          const unsigned rest = vmask & ~__ballot_sync(0xffffffffu, inA);
-          if (rest == 0) {
-            pmode = 0;
-          } else {
-            laneB = __ffs(rest) - 1;
-            const int nodeB = __shfl_sync(0xffffffffu, nd, laneB);
-            inB = (nd == nodeB);
-            krowB = kb + nodeB;
-            pmode = ((rest & ~__ballot_sync(0xffffffffu, inB)) == 0) ? 1 : 2;
+            for (int c = 0; c < 6; ++c) a = fmaf(w[c], xn[c], a);
+            y[i] = fminf(fmaxf(a, 0.f), 65504.f);
           }
+          uint32_t wds[16];
+          tc::split16_f16(y, wds);
+          tc::st16(lane_base + COL_A0 + ch0, wds);
         }
-      }
-      for (int nc = 0; nc < L3_CHUNKS; ++nc) {
-        const int buf = nc & 1;
-        tc::mbar_wait_bounded(&d3full[buf], (nc >> 1) & 1, 22);   // two uses per tile: parity = use&1
-        tc::fence_after_sync();
-        if (warp == 4) PM_TL(1, 6 + 2 * nc);
-        uint32_t v0[16], v1[16], v2[16];
-        const uint32_t cb = lane_base + COL_D3 + L3_N * buf + 48 * h;
-        tc::ld16(cb, v0);
-        tc::ld16(cb + 16, v1);
-        tc::ld16(cb + 32, v2);
-        tc::wait_ld();
+        tc::wait_st();
         tc::fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&d3empty[buf]);
-        if (nc == L3_CHUNKS - 1 && t + 1 < my_tiles) {
-          if (warp == 4) PM_TL(1, 0);
-          layer0();                                // next tile's layer 0 first, then this chunk's work
-        }
+        if (lane == 0) mbar_arrive(b_act0);
+        if (warp == 4) PM_TL(1, 1);
+        // this tile's node ids / copy-0 row: their L2 latency hides behind layers 1-2
         if (POOL) {
-          const int co0 = L3_N * nc + 48 * h;
-          // value -> order-preserving int key; lanes outside `in` contribute the identity
-          auto keyof = [&](uint32_t raw, int co, float& val) {
-            val = fmaf(__uint_as_float(raw), inv3, sh3[co]);
-            const int bits = __float_as_int(val);
-            return bits ^ ((bits >> 31) & 0x7fffffff);
-          };
-          // Per-node max of 16 channels over the warp's 32 rows as a shuffle transpose-reduce:
-          // recursive halving (xor 16, 8, 4, 2, then 1) leaves the max of channel
-          // c(lane) = lane bits 4..1 (bit 4 = MSB) in every lane pair after 16 shuffles — one
-          // per channel — and the even lanes issue ONE 16-lane red. (48 redux.sync per chunk
-          // serialise on two uniform registers: measured 4.7-5.8k cycles per chunk, longer than the
-          // chunk's MMAs, and the busy epilogue warps starved the MMA warp of issue slots.)
-          auto tmax16 = [&](const int (&k16)[16]) {
-            int a8[8], b4[4], c2[2];
-            {
-              const bool hi = (lane & 16) != 0;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int keep = hi ? k16[8 + i] : k16[i], send = hi ? k16[i] : k16[8 + i];
-                a8[i] = max(keep, __shfl_xor_sync(0xffffffffu, send, 16));
-              }
-            }
-            {
-              const bool hi = (lane & 8) != 0;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int keep = hi ? a8[4 + i] : a8[i], send = hi ? a8[i] : a8[4 + i];
-                b4[i] = max(keep, __shfl_xor_sync(0xffffffffu, send, 8));
-              }
-            }
-            {
-              const bool hi = (lane & 4) != 0;
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                const int keep = hi ? b4[2 + i] : b4[i], send = hi ? b4[i] : b4[2 + i];
-                c2[i] = max(keep, __shfl_xor_sync(0xffffffffu, send, 4));
-              }
-            }
-            const bool hi = (lane & 2) != 0;
-            const int keep = hi ? c2[1] : c2[0], send = hi ? c2[0] : c2[1];
-            const int d1 = max(keep, __shfl_xor_sync(0xffffffffu, send, 2));
-            return max(d1, __shfl_xor_sync(0xffffffffu, d1, 1));
-          };
-          const int my_chan = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
-                              ((lane >> 1) & 1);
-          auto pool_group = [&](const uint32_t (&v)[16], int cbase) {
-            if (pmode == 0 || pmode == 1) {
-              int keys[16], ka[16];
-              float vals;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                keys[i] = keyof(v[i], cbase + i, vals);
-                ka[i] = inA ? keys[i] : POOL_KEY_MIN;
-              }
-              int mine = tmax16(ka);
-              if (pmode == 1) {        // warp-uniform and rare: a node boundary inside the warp
-                int kb[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) kb[i] = inB ? keys[i] : POOL_KEY_MIN;
-                const int mb = tmax16(kb);
-                mine = (lane & 1) ? mb : mine;     // odd lanes carry the second node's maxima
-              }
-              if (!(lane & 1) || pmode == 1) {
-                int32_t* dst = ((lane & 1) ? krowB : krowA) +
-                               static_cast<size_t>(cbase + my_chan) * pool.M;
-                atomicMax(dst, mine);
-              }
-            } else if (pmode == 2) {   // three or more nodes in one warp (tiny nodes): per lane
-              float vals;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int key = keyof(v[i], cbase + i, vals);
-                if (nd >= 0) atomicMax(krow + static_cast<size_t>(cbase + i) * pool.M, key);
-              }
-            }
-            if (any_p0) {              // warp-uniform and rare: one warp per cloud and column half
-              if (is_p0) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  pool.p0[static_cast<size_t>(b) * C3 + cbase + i] =
-                      fmaf(__uint_as_float(v[i]), inv3, sh3[cbase + i]);
-              }
-            }
-          };
-          pool_group(v0, co0);
-          pool_group(v1, co0 + 16);
-          pool_group(v2, co0 + 32);
-        } else if (valid) {
-          const int co0 = L3_N * nc + 48 * h;
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            orow[static_cast<size_t>(co0 + i) * P] = fmaf(__uint_as_float(v0[i]), inv3, sh3[co0 + i]);
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            orow[static_cast<size_t>(co0 + 16 + i) * P] =
-                fmaf(__uint_as_float(v1[i]), inv3, sh3[co0 + 16 + i]);
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            orow[static_cast<size_t>(co0 + 32 + i) * P] =
-                fmaf(__uint_as_float(v2[i]), inv3, sh3[co0 + 32 + i]);
+          if (valid) nd_next = __ldg(pool.node_sorted + static_cast<size_t>(b) * P + j);
+          p0row = __ldg(pool.pos0 + b);
         }
-        if (warp == 4) PM_TL(1, 7 + 2 * nc);
+
+        // ---- layer 1 epilogue, in place: K slab kc of layer 2 = act1 channels [32kc, 32kc+32),
+        // 16 per warpgroup, announced slab by slab ----
+        tc::mbar_wait_bounded(b_d1, par, 20);
+        tc::fence_after_sync();
+        if (warp == 4) PM_TL(1, 2);
+#pragma unroll 1
+        for (int kc = 0; kc < 4; ++kc) {
+          const int ch0 = 32 * kc + 16 * h;
+          uint32_t v[16];
+          tc::ld16(lane_base + COL_D1 + ch0, v);
+          tc::wait_ld();
+          float y[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            y[i] = fminf(fmaxf(fmaf(__uint_as_float(v[i]), inv1, sh1[ch0 + i]), 0.f), 65504.f);
+          tc::split16_f16(y, v);
+          tc::st16(lane_base + COL_D1 + ch0, v);
+          tc::wait_st();
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&b_act1s[kc]);
+        }
+        if (warp == 4) PM_TL(1, 3);
+
       }
+
+      // ---- layer 3 epilogue: four chunks of 96 channels, 48 per warpgroup; bare layer (no ReLU) ----
+      const int nc_end = live ? L3_CHUNKS : 0;
+#pragma unroll 1
+      for (int nc = -1; nc < nc_end; ++nc) {
+        if (nc == 0) {                  // from here on the chunks belong to tile t
+          cx_b = b;
+          cx_valid = valid;
+          cx_orow = POOL ? nullptr : out + (static_cast<size_t>(b) * C3) * P + j;
+          if (POOL) {
+            cx_nd = nd_next;
+            cx_vmask = __ballot_sync(FULL, nd_next >= 0);
+            cx_is_p0 = valid && (j == p0row);
+            cx_any_p0 = __any_sync(FULL, cx_is_p0);
+          }
+        }
+        if (nc >= 0) {
+          const int buf = nc & 1;
+          tc::mbar_wait_bounded(&d3full[buf], (nc >> 1) & 1, 22);   // two uses per tile: parity = use&1
+          tc::fence_after_sync();
+          if (warp == 4) PM_TL(1, 6 + 2 * nc);
+          const uint32_t cb = lane_base + COL_D3 + L3_N * buf + 48 * h;
+          tc::ld16(cb, v0);
+          tc::ld16(cb + 16, v1);
+          tc::ld16(cb + 32, v2);
+          tc::wait_ld();
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&d3empty[buf]);
+        }
+        const bool finish = (nc < 0) ? parked : (nc < L3_CHUNKS - 1);
+        if (finish) {
+          const int co0 = L3_N * (nc < 0 ? L3_CHUNKS - 1 : nc) + 48 * h;
+          if (POOL) {
+            pool_group(v0, co0);
+            pool_group(v1, co0 + 16);
+            pool_group(v2, co0 + 32);
+          } else if (cx_valid) {
+            store_group(v0, co0);
+            store_group(v1, co0 + 16);
+            store_group(v2, co0 + 32);
+          }
+          if (warp == 4) PM_TL(1, nc < 0 ? 13 : 7 + 2 * nc);
+        }
+        if (nc < 0 && live) {
+          // (the parked chunk of tile t-1 was pooled just above, inside the window in which this
+          // tile's layer-2 MMAs run and the epilogue warps would otherwise wait for b_d2)
+          // ---- layer 2 epilogue, in place: quarter qd = act2 channels [64qd, 64qd+64) = K stage
+          // qd+1 of layer 3, 32 per warpgroup (two groups of 16), announced quarter by quarter ----
+          tc::mbar_wait_bounded(b_d2, par, 21);
+          tc::fence_after_sync();
+          if (warp == 4) PM_TL(1, 4);
+#pragma unroll 1
+          for (int g = 0; g < 8; ++g) {
+            const int qd = g >> 1;
+            const int ch0 = 64 * qd + 32 * h + 16 * (g & 1);
+            uint32_t v[16];
+            tc::ld16(lane_base + COL_D2 + ch0, v);
+            tc::wait_ld();
+            float y[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              y[i] = fminf(fmaxf(fmaf(__uint_as_float(v[i]), inv2, sh2[ch0 + i]), 0.f), 65504.f);
+            tc::split16_f16(y, v);
+            tc::st16(lane_base + COL_D2 + ch0, v);
+            if (g & 1) {
+              tc::wait_st();
+              tc::fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&b_act2q[qd]);
+            }
+          }
+          if (warp == 4) PM_TL(1, 5);
+          if (t + 1 < my_tiles) prefetch_x(t + 1);   // in flight during the layer-3 MMAs
+        }
+      }
+      parked = live;
     }
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) dbg[64 + 63] = clock64();
   if (CL > 1) tc::cluster_sync_all();   // no CTA leaves while peers may still signal its barriers
   if (warp == 2) tc::tmem_dealloc(tm, 512);
 #undef PM_TL

@@ -132,6 +132,71 @@ __device__ __forceinline__ void mma_ts_elect(uint32_t d_tmem, uint32_t a_tmem, u
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The three products of one fp16 hi/lo split K step — hi(a)*hi(b), lo(a)*hi(b), hi(a)*lo(b) —
+// behind ONE elect: a third of the ELECT/VOTE traffic of three mma_ts_elect calls on the issuing
+// warp, whose instruction stream is what bounds layer 3 when the epilogue warps are busy.
+__device__ __forceinline__ void mma_ts_elect3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo,
+                                              uint64_t b_hi, uint64_t b_lo, uint32_t idesc,
+                                              uint32_t accumulate_first) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, e, t;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %3, %5, p;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], %3, %5, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %4, %5, t;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_hi), "r"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate_first)
+      : "memory");
+}
+// One K STAGE of the split product — KS k-steps of 16, three MMAs each — behind ONE elect, with
+// the running TMEM / descriptor addresses advanced inside the PTX block. ptxas then keeps them in
+// the uniform datapath (UIADD3 + UTCHMMA, ~4 instructions per MMA); one asm statement per MMA cost
+// four R2UR.BROADCAST plus votes per MMA (~50 issue cycles, more than an N=96 MMA executes).
+// a0: TMEM address of the first hi column group (lo = +8, next k-step = +16);
+// bh0/bl0: descriptors of the hi/lo weight images (next k-step = +16 encoded = +256 B).
+#define SONET_MMA3 \
+  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [ah], bh, %4, t;\n" \
+  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [al], bh, %4, t;\n" \
+  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [ah], bl, %4, t;\n"
+#define SONET_ADV \
+  "add.u32 ah, ah, 16;\n add.u32 al, al, 16;\n add.u64 bh, bh, 16;\n add.u64 bl, bl, 16;\n"
+#define SONET_STAGE_HEAD \
+  "{\n" \
+  ".reg .pred p, e, t;\n" \
+  ".reg .b32 ah, al;\n" \
+  ".reg .b64 bh, bl;\n" \
+  "setp.ne.b32 p, %5, 0;\n" \
+  "setp.eq.b32 t, 0, 0;\n" \
+  "elect.sync _|e, 0xffffffff;\n" \
+  "mov.b32 ah, %1;\n" \
+  "add.u32 al, ah, 8;\n" \
+  "mov.b64 bh, %2;\n" \
+  "mov.b64 bl, %3;\n" \
+  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [ah], bh, %4, p;\n" \
+  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [al], bh, %4, t;\n" \
+  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [ah], bl, %4, t;\n"
+template <int KS>
+__device__ __forceinline__ void mma_ts_stage(uint32_t d_tmem, uint32_t a0, uint64_t bh0,
+                                             uint64_t bl0, uint32_t idesc,
+                                             uint32_t accumulate_first) {
+  static_assert(KS == 2 || KS == 4, "mma_ts_stage: 2 or 4 k-steps");
+  if constexpr (KS == 2) {
+    asm volatile(SONET_STAGE_HEAD SONET_ADV SONET_MMA3 "}\n" ::"r"(d_tmem), "r"(a0), "l"(bh0),
+                 "l"(bl0), "r"(idesc), "r"(accumulate_first)
+                 : "memory");
+  } else {
+    asm volatile(SONET_STAGE_HEAD SONET_ADV SONET_MMA3 SONET_ADV SONET_MMA3 SONET_ADV SONET_MMA3
+                 "}\n" ::"r"(d_tmem),
+                 "r"(a0), "l"(bh0), "l"(bl0), "r"(idesc), "r"(accumulate_first)
+                 : "memory");
+  }
+}
+#undef SONET_MMA3
+#undef SONET_ADV
+#undef SONET_STAGE_HEAD
 __device__ __forceinline__ void mma_ss_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                              uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -221,9 +286,42 @@ __device__ __forceinline__ void split16_f16(const float (&x)[16], uint32_t (&out
 }
 
 // bounded mbarrier wait: a protocol bug traps instead of hanging the GPU box
+static __device__ __noinline__ void mbar_timeout(int tag, uint32_t parity) {
+  printf("[sonet] mbarrier wait timed out: tag %d block %d thread %d parity %u\n", tag,
+         (int)blockIdx.x, (int)threadIdx.x, parity);
+  __trap();
+}
+// Spin on the barrier phase; traps (instead of hanging the GPU) after 2^24 failed try_waits.
+// The whole loop is ONE asm statement: a C-level loop on the try_wait result is a divergent loop
+// in the compiler's eyes (it was also unrolled 64x — 2 KB of code per wait site — before
+// `#pragma unroll 1`), and values live across it fall out of the uniform datapath, which the MMA
+// issuing warp needs for its descriptors. A timeout traps (cudaErrorLaunchFailure on the host).
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity, int tag) {
+  (void)tag;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .u32 c;\n"
+      "mov.u32 c, 0;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "add.u32 c, c, 1;\n"
+      "setp.lt.u32 p, c, 0x1000000;\n"
+      "@p bra WAIT_%=;\n"
+      "trap;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// Same for waiters that are never latency-critical (a TMA producer running slots ahead): back off
+// between polls so the spin does not take issue slots from the warps sharing the sub-partition.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int tag) {
   uint32_t done = 0;
-  for (uint32_t it = 0; it < (1u << 24); ++it) {
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 22); ++it) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -234,10 +332,9 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     if (done) return;
+    __nanosleep(100);
   }
-  printf("[sonet] mbarrier wait timed out: tag %d block %d thread %d parity %u\n", tag,
-         (int)blockIdx.x, (int)threadIdx.x, parity);
-  __trap();
+  mbar_timeout(tag, parity);
 }
 
 }  // namespace tc

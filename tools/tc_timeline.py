@@ -18,7 +18,8 @@ with torch.no_grad():
     net(x)
     blob, fpar = net._tc_params()
     out = torch.empty(64, 384, 15000, device="cuda")
-    tl = torch.zeros(64, dtype=torch.int64, device="cuda")
+    tl = torch.zeros(128, dtype=torch.int64, device="cuda")
+    tl[125] = int(sys.argv[sys.argv.index("--tile") + 1]) if "--tile" in sys.argv else 3
     if "--pool" in sys.argv:
         from sonet_b200 import ops, synth as _s
         inp = _s.synth_inputs(64, 5000, seed=0)
@@ -39,7 +40,13 @@ with torch.no_grad():
                 tl.data_ptr(), None), "timeline")
     torch.cuda.synchronize()
 t = tl.cpu().tolist()
-mma, epi = t[:32], t[32:]
+starts = [v for v in t[64:124] if v > 0]
+if starts:
+    k0, k1 = t[64 + 62], t[64 + 63]
+    print("CTA 0: kernel %d cycles, %d tiles; first act0-ready at +%d, last at +%d (end +%d after it)"
+          % (k1 - k0, len(starts), starts[0] - k0, starts[-1] - k0, k1 - starts[-1]))
+    print("tile periods:", [b - a for a, b in zip(starts, starts[1:])])
+mma, epi = t[:32], t[32:64]
 t0 = min(v for v in (mma[:13] + epi[:14]) if v > 0)
 names_m = ["act0 ready", "L1 issued", "act1 ready", "L2 issued", "act2 ready"] + \
     [s for nc in range(4) for s in ("c%d start" % nc, "c%d issued" % nc)]
