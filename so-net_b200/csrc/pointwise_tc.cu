@@ -9,10 +9,13 @@
 //
 // Rows (b,p) are flattened and tiled by 128 = MMA M = TMEM lanes; an item is (row tile, 256-wide
 // out-channel tile); K streams in 64-channel chunks through a 2-stage ring:
-//   * converter warps (8): fetch the fp32 activations with cp.async into a staging buffer (thread = row,
-//     coalesced along p, whole chunk in flight), clamp to the
-//     fp16 range, split into fp16 hi/lo and write the K-major no-swizzle A images with one 128-bit
-//     shared store per 8 channels (conflict free), fence.proxy.async, arrive;
+//   * converter warps (8): fetch the fp32 activations with cp.async into a staging buffer — 16 B
+//     per thread (4 consecutive rows of one channel: a warp instruction moves one channel's 128
+//     rows) when P and the base pointers allow it, 4 B otherwise; LDGSTS costs ~8 LSU cycles per
+//     warp instruction whatever its width, and at 4 B the 256 instructions of a chunk took longer
+//     than its MMAs — then clamp to the fp16 range, split into fp16 hi/lo and write the K-major
+//     no-swizzle A images with one 128-bit shared store per 8 channels (conflict free),
+//     fence.proxy.async, arrive;
 //   * TMA warp: streams the pre-packed fp16 hi/lo weight images (cp.async.bulk + mbarrier);
 //   * MMA warp (one thread): 3 tcgen05.mma.kind::f16 per 16-channel K step (hi*hi + lo*hi + hi*lo),
 //     SS mode, M=128, N<=256, fp32 accumulation in TMEM, two 256-column accumulator buffers so the
@@ -46,6 +49,7 @@ struct Dims {
   int kchunks;   // ceil(pad16(Cin) / 64)
   int ntiles;    // out-channel tiles of <= 256 (each a multiple of 64)
   int cin_pad;   // Cin rounded up to 16
+  int vec4;      // 16-byte activation fetch is legal (P % 4 == 0, 16-byte aligned bases)
   float inv;     // 1 / weight pre-scale
 };
 __host__ __device__ inline int ntile_width(int Cout, int nt) {
@@ -75,7 +79,9 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
   uint64_t* d_empty = d_full + 2;           // [2] epilogue -> MMA
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: ptxas then knows the role branches are warp-uniform
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
   const long long rows = static_cast<long long>(d.B) * d.P;
   const int row_tiles = static_cast<int>((rows + TILE - 1) / TILE);
   const int items = row_tiles * d.ntiles;   // n-tile fastest: the activation tile stays hot in L2
@@ -102,7 +108,8 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tm = *tmem_ptr;
+  if (*tmem_ptr != 0u) __trap();   // all 512 columns allocated: the base is 0 by construction
+  constexpr uint32_t tm = 0;
 
   if (warp == 0) {
     // ================= TMA producer: weight chunk images =================
@@ -117,7 +124,7 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
         const uint32_t bytes = static_cast<uint32_t>(nw) * KCH * 4;
         for (int kc = 0; kc < d.kchunks; ++kc, ++q) {
           const uint32_t slot = q % NSTAGE, use = q / NSTAGE;
-          if (use > 0) tc::mbar_wait_bounded(&empty[slot], (use - 1) & 1, 200);
+          if (use > 0) tc::mbar_wait_relaxed(&empty[slot], (use - 1) & 1, 200);
           mbar_arrive_expect_tx(&full_w[slot], bytes);
           bulk_g2s(smem + OFF_W + slot * W_BYTES, blob + off, bytes, &full_w[slot]);
           if (it == 0) PW_TL(0, kc);
@@ -128,7 +135,8 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
   } else if (warp == 1) {
     // ========== MMA issuer: converged warp, elect.sync issues from one lane ==========
     {
-      const uint32_t a_base = smem_u32(smem + OFF_A), w_base = smem_u32(smem + OFF_W);
+      const uint32_t a_base = static_cast<uint32_t>(__cvta_generic_to_shared(smem + OFF_A)),
+                     w_base = static_cast<uint32_t>(__cvta_generic_to_shared(smem + OFF_W));
       uint32_t q = 0;
       for (int it = 0; it < my_items; ++it) {
         const int item = blockIdx.x + it * gridDim.x;
@@ -149,15 +157,13 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
           if (it == 0) PW_TL(1, 3 * kc + 1);
           const uint32_t as = a_base + slot * A_BYTES, ws = w_base + slot * W_BYTES;
           const int nks = min(4, (d.cin_pad - kc * KCH) / 16);
-          for (int ks = 0; ks < nks; ++ks) {
-            const uint64_t ah = tc::smem_desc(as + ks * 256, 128, 1024),
-                           al = tc::smem_desc(as + A_BYTES / 2 + ks * 256, 128, 1024),
-                           bh = tc::smem_desc(ws + ks * 256, 128, 1024),
-                           bl = tc::smem_desc(ws + nw * KCH * 2 + ks * 256, 128, 1024);
-            tc::mma_ss_elect(dcol, ah, bh, idesc, (kc | ks) != 0);
-            tc::mma_ss_elect(dcol, al, bh, idesc, 1);
-            tc::mma_ss_elect(dcol, ah, bl, idesc, 1);
-          }
+          const uint64_t ah = tc::smem_desc(as, 128, 1024), al = tc::smem_desc(as + A_BYTES / 2, 128, 1024),
+                         bh = tc::smem_desc(ws, 128, 1024),
+                         bl = tc::smem_desc(ws + nw * KCH * 2, 128, 1024);
+          if (nks == 4) tc::mma_ss_stage<4>(dcol, ah, al, bh, bl, idesc, kc != 0);
+          else if (nks == 3) tc::mma_ss_stage<3>(dcol, ah, al, bh, bl, idesc, kc != 0);
+          else if (nks == 2) tc::mma_ss_stage<2>(dcol, ah, al, bh, bl, idesc, kc != 0);
+          else tc::mma_ss_stage<1>(dcol, ah, al, bh, bl, idesc, kc != 0);
           tc::commit_elect(&empty[slot]);
           if (it == 0) PW_TL(1, 3 * kc + 2);
         }
@@ -168,46 +174,74 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
     // ================= converters: fp32 activations -> fp16 hi/lo K-major A images =================
     const int t = threadIdx.x - 384;
     const int m = t & 127, half = t >> 7;   // row in tile; which 32 of the chunk's 64 channels
-    // The fp32 activations of a chunk are fetched with cp.async (LDGSTS, 4 B per thread and
-    // channel: a warp copies 128 contiguous bytes) into a staging buffer [64 ch][128 rows]: the
-    // whole 32 KB chunk is in flight without holding registers. (Register-staged loads were
-    // bytes-in-flight bound: 16-32 loads per thread -> 4-5k cycles per chunk in the timeline.)
-    // Every thread later reads back exactly the elements it copied, so cp.async.wait_group is
-    // the only synchronisation needed; the next chunk's copies are issued as soon as the
-    // current values are in registers.
+    // The fp32 activations of a chunk are fetched with cp.async (LDGSTS) into a staging buffer
+    // [64 ch][128 rows]: the whole 32 KB chunk is in flight without holding registers.
+    // (Register-staged loads were bytes-in-flight bound: 4-5k cycles per chunk in the timeline.)
+    // Each thread converts row m's 32 channels, which other threads copied: wait_group + a named
+    // barrier before the read, another one before the tile is refilled with the next chunk.
     const uint32_t total = static_cast<uint32_t>(my_items) * d.kchunks;
     float* stg = reinterpret_cast<float*>(smem + OFF_STG) + (half * 32) * TILE + m;
     const uint32_t stg_s = smem_u32(stg);
     auto issue = [&](uint32_t qq) {
       const int it = qq / d.kchunks, kc = qq - it * d.kchunks;
       const int item = blockIdx.x + it * gridDim.x;
-      const long long R = static_cast<long long>(item / d.ntiles) * TILE + m;
-      const bool valid = R < rows;
-      const int b = valid ? static_cast<int>(R / d.P) : 0;
-      const int p = valid ? static_cast<int>(R - static_cast<long long>(b) * d.P) : 0;
-      const float* r0 = x0 + static_cast<size_t>(b) * d.C0 * d.P + p;
-      const float* r1 = d.C1 ? x1 + static_cast<size_t>(b) * d.C1 * d.P + p : x0;
-      const int c_base = kc * KCH + half * 32;
+      const long long R0 = static_cast<long long>(item / d.ntiles) * TILE;
+      if (d.vec4) {
+        // warp w copies channels w, w+8, ..., w+56 of the chunk; lane l the rows 4l..4l+3 (never
+        // across a cloud boundary because P % 4 == 0)
+        const long long R = R0 + 4 * lane;
+        const bool valid = R < rows;
+        const int b = valid ? static_cast<int>(R / d.P) : 0;
+        const int p = valid ? static_cast<int>(R - static_cast<long long>(b) * d.P) : 0;
+        const float* r0 = x0 + static_cast<size_t>(b) * d.C0 * d.P + p;
+        const float* r1 = d.C1 ? x1 + static_cast<size_t>(b) * d.C1 * d.P + p : x0;
+        const int w8 = (t >> 5);
+        const uint32_t dst0 = smem_u32(smem + OFF_STG) + (w8 * TILE + 4 * lane) * 4;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int ci = c_base + i;
-        const bool ok = valid && ci < Cin;
-        const float* src = !ok ? x0
-                               : (ci < d.C0 ? r0 + static_cast<size_t>(ci) * d.P
-                                            : r1 + static_cast<size_t>(ci - d.C0) * d.P);
-        const uint32_t nbytes = ok ? 4u : 0u;   // 0 -> zero fill
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(stg_s + i * TILE * 4),
-                     "l"(src), "r"(nbytes)
-                     : "memory");
+        for (int i = 0; i < 8; ++i) {
+          const int ci = kc * KCH + w8 + 8 * i;
+          const bool ok = valid && ci < Cin;
+          const float* src = !ok ? x0
+                                 : (ci < d.C0 ? r0 + static_cast<size_t>(ci) * d.P
+                                              : r1 + static_cast<size_t>(ci - d.C0) * d.P);
+          const uint32_t nbytes = ok ? 16u : 0u;   // 0 -> zero fill
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + i * 8 * TILE * 4),
+                       "l"(src), "r"(nbytes)
+                       : "memory");
+        }
+      } else {
+        const long long R = R0 + m;
+        const bool valid = R < rows;
+        const int b = valid ? static_cast<int>(R / d.P) : 0;
+        const int p = valid ? static_cast<int>(R - static_cast<long long>(b) * d.P) : 0;
+        const float* r0 = x0 + static_cast<size_t>(b) * d.C0 * d.P + p;
+        const float* r1 = d.C1 ? x1 + static_cast<size_t>(b) * d.C1 * d.P + p : x0;
+        const int c_base = kc * KCH + half * 32;
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+          const int ci = c_base + i;
+          const bool ok = valid && ci < Cin;
+          const float* src = !ok ? x0
+                                 : (ci < d.C0 ? r0 + static_cast<size_t>(ci) * d.P
+                                              : r1 + static_cast<size_t>(ci - d.C0) * d.P);
+          const uint32_t nbytes = ok ? 4u : 0u;   // 0 -> zero fill
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(stg_s + i * TILE * 4),
+                       "l"(src), "r"(nbytes)
+                       : "memory");
+        }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // the 256 converter threads exchange data through the staging tile: named barrier 1
+    auto conv_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     if (total > 0) issue(0);
     for (uint32_t qq = 0; qq < total; ++qq) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
+      conv_sync();                          // every thread's copies have landed
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = stg[i * TILE];
+      conv_sync();                          // the staging tile has been read: refill it
       if (qq + 1 < total) issue(qq + 1);
       const uint32_t slot = qq % NSTAGE, use = qq / NSTAGE;
       if (use > 0) tc::mbar_wait_bounded(&empty[slot], (use - 1) & 1, 204);
@@ -375,6 +409,7 @@ static int launch_pointwise_tc(const float* x0, int C0, const float* x1, int C1,
   d.kchunks = (d.cin_pad + KCH - 1) / KCH;
   d.ntiles = ((Cout + 63) / 64 * 64 + NT - 1) / NT;
   d.inv = inv_scale;
+  d.vec4 = (P % 4 == 0) && aligned16(x0) && (C1 == 0 || aligned16(x1));
   const long long rows = static_cast<long long>(B) * P;
   const long long items = (rows + TILE - 1) / TILE * d.ntiles;
   SONET_REQUIRE(items < (1LL << 31), "pointwise_tc: too many tiles");

@@ -197,6 +197,46 @@ __device__ __forceinline__ void mma_ts_stage(uint32_t d_tmem, uint32_t a0, uint6
 #undef SONET_MMA3
 #undef SONET_ADV
 #undef SONET_STAGE_HEAD
+// SS-mode K stage: NKS k-steps (1..4) of the split product, A and B images in shared memory, one
+// elect; descriptors advance by +16 encoded (= 256 B = one 16-wide k-step) inside the block.
+template <int NKS>
+__device__ __forceinline__ void mma_ss_stage(uint32_t d_tmem, uint64_t ah0, uint64_t al0,
+                                             uint64_t bh0, uint64_t bl0, uint32_t idesc,
+                                             uint32_t accumulate_first) {
+  static_assert(NKS >= 1 && NKS <= 4, "mma_ss_stage: 1..4 k-steps");
+#define SONET_SS3(P0)                                                   \
+  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bh, %5, " P0 ";\n" \
+  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], al, bh, %5, t;\n"      \
+  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bl, %5, t;\n"
+#define SONET_SSADV \
+  "add.u64 ah, ah, 16;\n add.u64 al, al, 16;\n add.u64 bh, bh, 16;\n add.u64 bl, bl, 16;\n"
+#define SONET_SSHEAD               \
+  "{\n"                           \
+  ".reg .pred p, e, t;\n"         \
+  ".reg .b64 ah, al, bh, bl;\n"   \
+  "setp.ne.b32 p, %6, 0;\n"       \
+  "setp.eq.b32 t, 0, 0;\n"        \
+  "elect.sync _|e, 0xffffffff;\n" \
+  "mov.b64 ah, %1;\n mov.b64 al, %2;\n mov.b64 bh, %3;\n mov.b64 bl, %4;\n"
+#define SONET_SSOPS                                                                          \
+  ::"r"(d_tmem), "l"(ah0), "l"(al0), "l"(bh0), "l"(bl0), "r"(idesc), "r"(accumulate_first) \
+      : "memory"
+  if constexpr (NKS == 1) {
+    asm volatile(SONET_SSHEAD SONET_SS3("p") "}\n" SONET_SSOPS);
+  } else if constexpr (NKS == 2) {
+    asm volatile(SONET_SSHEAD SONET_SS3("p") SONET_SSADV SONET_SS3("t") "}\n" SONET_SSOPS);
+  } else if constexpr (NKS == 3) {
+    asm volatile(SONET_SSHEAD SONET_SS3("p") SONET_SSADV SONET_SS3("t") SONET_SSADV SONET_SS3("t")
+                 "}\n" SONET_SSOPS);
+  } else {
+    asm volatile(SONET_SSHEAD SONET_SS3("p") SONET_SSADV SONET_SS3("t") SONET_SSADV SONET_SS3("t")
+                     SONET_SSADV SONET_SS3("t") "}\n" SONET_SSOPS);
+  }
+#undef SONET_SS3
+#undef SONET_SSADV
+#undef SONET_SSHEAD
+#undef SONET_SSOPS
+}
 __device__ __forceinline__ void mma_ss_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                              uint32_t idesc, uint32_t accumulate) {
   asm volatile(
