@@ -189,6 +189,26 @@ int sonet_pointresnet_tc_pack(const float* W0, int Cin, const float* W1, const f
 int sonet_pointresnet_tc_forward(const float* x, int Cin, int B, int P, const void* blob,
                                  const float* fparams, float* out, sonet_stream_t stream);
 
+/* Classifier-path fusion of the cluster statistics (models/networks.py:140-143), the node sort and
+ * the decentring (networks.py:168-172) in ONE launch: a stable counting sort of the k*N stacked
+ * copies by node, per-node coordinate sums in that fixed order (bit-reproducible, independent of
+ * batch sharding), cluster_mean = sum / (count + 1e-5), then x_sorted / node_sorted / pos0 exactly
+ * as sonet_som_sort_decenter defines them (rows of a node in ascending stacked order).
+ * count [B,M] i32, cluster_mean [B,3,M] are outputs. Needs sonet_som_group_smem_bytes(N,M,k)
+ * bytes of shared memory per block (4*k*N + small); fails with a message beyond the device limit. */
+long long sonet_som_group_smem_bytes(int N, int M, int k);
+int sonet_som_group_decenter(const float* x, const float* sn, const int32_t* min_idx_i32, int B,
+                             int N, int M, int k, int32_t* count, float* cluster_mean,
+                             float* x_sorted, int32_t* node_sorted, int32_t* pos0,
+                             sonet_stream_t stream);
+/* KNNModule input assembly (models/layers.py:346-361) directly from the fused pool's keys:
+ * sonet_pool_finalize folded into sonet_knn_assemble_f32. Writes masked_max [B,C,M]
+ * (first_pn_out_masked_max, models/networks.py:185), center [B,3,M], x_aug [B,3+C,M*K] and
+ * resets the keys. M <= 256 and M*K <= 2304. */
+int sonet_knn_assemble_pool_f32(const float* coord, int32_t* pool_keys, const float* p0,
+                                const int64_t* idx, int B, int C, int M, int K, int Kstride,
+                                int center_type, float* masked_max, float* center, float* x_aug,
+                                sonet_stream_t stream);
 /* ---- a-3 + a-5 + a-6/a-7 fused: node-sorted copies -> tcgen05 PointResNet -> per-node max -----
  * The classifier / auto-encoder path, where first_pn_out [B,384,kN] itself is never needed
  * (models/networks.py:168-185): it is neither written nor re-read.

@@ -33,6 +33,15 @@ int max_smem_optin();     // cached max opt-in dynamic shared memory per block
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- device helpers ---------------------------------------------------------------------------
+// Running per-node maxima of the fused pool (csrc/pointmlp_tc.cu) are order-preserving int keys.
+constexpr int POOL_KEY_INIT = static_cast<int>(0x80000000u);  // below the key of every float
+// key -> value with the reference's semantics: the max must be > -1000 (index_max.cpp:80-81,103),
+// otherwise the node gathers the feature of stacked copy 0 (models/networks.py:185).
+__device__ __forceinline__ float pool_key_value(int key, float p0v) {
+  const int bits = key ^ ((key >> 31) & 0x7fffffff);
+  const float v = __int_as_float(bits);
+  return (key != POOL_KEY_INIT && v > -1000.0f) ? v : p0v;
+}
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"

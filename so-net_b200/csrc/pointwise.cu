@@ -305,6 +305,65 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Same assembly for the fused-pool path, reading the per-node maxima straight from the pool keys:
+// pool_finalize (key -> value, empty node -> feature of copy 0, key reset) is folded in, so the
+// [B,C,M] maxima are written once (first_pn_out_masked_max, an Encoder attribute) and gathered
+// from shared memory. CTA = (channel group, cloud); threads run over the M*K output columns, so
+// the inner loop has no divisions and its stores are coalesced.
+constexpr int KA_CPB = 8;        // channels per CTA
+constexpr int KA_MAX_MK = 2304;  // M*K positions cached per CTA
+
+__global__ void __launch_bounds__(256)
+    knn_assemble_pool_kernel(const float* __restrict__ coord, int32_t* __restrict__ keys,
+                             const float* __restrict__ p0, const int64_t* __restrict__ idx, int C,
+                             int M, int K, int Kstride, int center_type,
+                             float* __restrict__ masked_max, float* __restrict__ center,
+                             float* __restrict__ x_aug) {
+  __shared__ float vals[KA_CPB * 256];          // [KA_CPB][M], M <= 256
+  __shared__ uint16_t sid[KA_MAX_MK];
+  const int b = blockIdx.y;
+  const int MK = M * K;
+  const int c0 = blockIdx.x * KA_CPB;
+  const int nc = min(KA_CPB, C - c0);
+  const int64_t* ib = idx + static_cast<size_t>(b) * M * Kstride;
+  for (int mj = threadIdx.x; mj < MK; mj += blockDim.x) {
+    const int m = mj / K, j = mj - m * K;
+    sid[mj] = static_cast<uint16_t>(clamp_idx(ib[m * Kstride + j], M));
+  }
+  for (int t = threadIdx.x; t < nc * M; t += blockDim.x) {
+    const int cl = t / M, m = t - cl * M;
+    const size_t g = (static_cast<size_t>(b) * C + c0 + cl) * M + m;
+    const float v = pool_key_value(keys[g], __ldg(p0 + static_cast<size_t>(b) * C + c0 + cl));
+    keys[g] = POOL_KEY_INIT;                      // ready for the next forward
+    masked_max[g] = v;
+    vals[cl * M + m] = v;
+  }
+  __syncthreads();
+  float* ob = x_aug + static_cast<size_t>(b) * (3 + C) * MK;
+  for (int cl = 0; cl < nc; ++cl) {
+    float* orow = ob + static_cast<size_t>(3 + c0 + cl) * MK;
+    const float* vrow = vals + cl * M;
+    for (int mj = threadIdx.x; mj < MK; mj += blockDim.x) orow[mj] = vrow[sid[mj]];
+  }
+  if (blockIdx.x == 0) {   // coordinates: thread per (c, m)
+    const float* cb = coord + static_cast<size_t>(b) * 3 * M;
+    for (int t = threadIdx.x; t < 3 * M; t += blockDim.x) {
+      const int c = t / M, m = t - c * M;
+      float ctr;
+      if (center_type == 0) {  // 'avg': torch.mean over K = sum / K
+        float s = 0.f;
+        for (int j = 0; j < K; ++j) s += cb[c * M + sid[m * K + j]];
+        ctr = __fdiv_rn(s, static_cast<float>(K));
+      } else {
+        ctr = cb[c * M + m];
+      }
+      center[(static_cast<size_t>(b) * 3 + c) * M + m] = ctr;
+      for (int j = 0; j < K; ++j)
+        ob[static_cast<size_t>(c) * MK + m * K + j] = __fsub_rn(cb[c * M + sid[m * K + j]], ctr);
+    }
+  }
+}
+
 // exact K-NN among the M nodes (models/layers.py:334-337): thread per (b, m).
 __global__ void __launch_bounds__(128)
     node_knn_kernel(const float* __restrict__ coord, int B, int M, int K,
@@ -460,6 +519,26 @@ extern "C" int sonet_knn_assemble_f32(const float* coord, const float* feat, con
   knn_assemble_kernel<<<grid, 256, 0, as_stream(stream)>>>(coord, feat, idx, C, M, K, Kstride,
                                                            center_type, center, x_aug);
   return check_launch("knn_assemble");
+}
+
+extern "C" int sonet_knn_assemble_pool_f32(const float* coord, int32_t* pool_keys, const float* p0,
+                                           const int64_t* idx, int B, int C, int M, int K,
+                                           int Kstride, int center_type, float* masked_max,
+                                           float* center, float* x_aug, sonet_stream_t stream) {
+  using namespace sonet;
+  SONET_REQUIRE(B >= 0 && C >= 1 && M >= 1 && K >= 1 && Kstride >= K,
+                "knn_assemble_pool: bad dimension");
+  SONET_REQUIRE(center_type == 0 || center_type == 1, "knn_assemble_pool: center_type %d", center_type);
+  SONET_REQUIRE(M <= 256 && static_cast<long long>(M) * K <= KA_MAX_MK,
+                "knn_assemble_pool: M=%d, K=%d exceed the per-CTA cache (finalize the pool and use "
+                "sonet_knn_assemble_f32)", M, K);
+  if (B == 0) return SONET_OK;
+  SONET_REQUIRE(coord && pool_keys && p0 && idx && masked_max && center && x_aug,
+                "knn_assemble_pool: null pointer");
+  dim3 grid(static_cast<unsigned>((C + KA_CPB - 1) / KA_CPB), B);
+  knn_assemble_pool_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+      coord, pool_keys, p0, idx, C, M, K, Kstride, center_type, masked_max, center, x_aug);
+  return check_launch("knn_assemble_pool");
 }
 
 extern "C" int sonet_node_knn(const float* coord, int B, int M, int K, int64_t* idx,

@@ -53,6 +53,11 @@ _SIGNATURES = {
                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "sonet_pointresnet_tc_pool_forward": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    "sonet_som_group_smem_bytes": [c_int, c_int, c_int],
+    "sonet_som_group_decenter": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sonet_knn_assemble_pool_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                    c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "sonet_pool_keys_init": [c_void_p, ctypes.c_longlong, c_void_p],
     "sonet_pool_finalize": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "sonet_pointwise_tc_blob_bytes": [c_int, c_int],
@@ -74,7 +79,8 @@ _SIGNATURES = {
     "sonet_version": [],
 }
 _RESTYPE = {"sonet_last_error_string": ctypes.c_char_p, "sonet_version": ctypes.c_char_p,
-            "sonet_pointwise_tc_blob_bytes": ctypes.c_longlong}
+            "sonet_pointwise_tc_blob_bytes": ctypes.c_longlong,
+            "sonet_som_group_smem_bytes": ctypes.c_longlong}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -339,13 +339,36 @@ class KNNModule(nn.Module):
                                         bn_momentum_decay=bn_momentum_decay))
             prev = c_out
 
+    def _fast(self, coordinate, x, precomputed_knn_I, center_type):
+        return (_fast_ok(self, coordinate, x) and center_type in ('avg', 'center')
+                and all(l._fast_eligible() for l in self.layers)
+                and (precomputed_knn_I is None or precomputed_knn_I.is_cuda))
+
+    def forward_pooled(self, coordinate, pool, precomputed_knn_I, K, center_type, epoch=None):
+        """forward() for the fused-pool path: `pool` = (keys [B,C,M] i32, p0 [B,C]) as left by
+        ops.pointresnet_tc_pool(finalize=False). Returns (center, feature, masked_max [B,C,M]) or
+        None when this module cannot take the fused route (the caller then finalizes the pool)."""
+        keys, p0 = pool
+        B, C, M = keys.shape
+        if not (self._fast(coordinate, p0, precomputed_knn_I, center_type)
+                and M <= 256 and M * K <= 2304):
+            return None
+        coord = coordinate.detach().contiguous()
+        if precomputed_knn_I is not None:
+            assert precomputed_knn_I.size()[2] >= K
+            knn_I = precomputed_knn_I.contiguous()
+        else:
+            knn_I = ops.node_knn(coord, K)
+        center, h, masked_max = ops.knn_assemble_pool(coord, keys, p0, knn_I, K, center_type)
+        for layer in self.layers:
+            h = layer.forward_points(h)
+        feature = ops.rowmax(h.view(B, h.shape[1], M, K))
+        return center, feature, masked_max
+
     def forward(self, coordinate, x, precomputed_knn_I, K, center_type, epoch=None):
         """coordinate [B,3,M], x [B,C,M], precomputed_knn_I [B,M,K'] -> (center [B,3,M],
         feature [B,Cout,M])."""
-        fast = (_fast_ok(self, coordinate, x) and center_type in ('avg', 'center')
-                and all(l._fast_eligible() for l in self.layers)
-                and (precomputed_knn_I is None or precomputed_knn_I.is_cuda))
-        if fast:
+        if self._fast(coordinate, x, precomputed_knn_I, center_type):
             coord = coordinate.detach().contiguous()
             if precomputed_knn_I is not None:
                 assert precomputed_knn_I.size()[2] >= K

@@ -149,27 +149,43 @@ class Encoder(nn.Module):
         # SOM nodes come from the loader (models/networks.py:123-124)
         self.som_builder.node = node.detach().to(torch.float32).contiguous()
 
-        # assignment + cluster statistics (networks.py:127-143) — always the CUDA kernel: the
+        # assignment + cluster statistics (networks.py:127-143) — always the CUDA kernels: the
         # reference computes these on .data (no gradient flows through them)
         xd = x.detach().contiguous()
-        a = ops.som_assign(xd, self.som_builder.node, k)
-        self._assign, self._mask, self._centers = a, None, None
+        snd = sn.detach().contiguous() if use_sn else None
+        fpn = self.first_pointnet
+        fused = (fast and self.fuse_pool and M <= 256 and fpn.layers[0].fast(xd)
+                 and fpn._tc_eligible(6 if use_sn else 3, None))
+        group = fused and ops.som_group_fits(xd.shape[2], M, k, xd.device)
+        a = ops.som_assign(xd, self.som_builder.node, k, want_stats=not group)
         idx32, mask_row_max = a["min_idx_i32"], a["row_max"]
+        if group:
+            # statistics + stable node sort + decentring in one launch
+            xs, ns, p0, a["count"], a["cluster_mean"] = ops.som_group_decenter(xd, snd, idx32, M, k)
+        self._assign, self._mask, self._centers = a, None, None
         self.som_builder.node = a["cluster_mean"]
         self.som_node = self.som_builder.node
 
-        snd = sn.detach().contiguous() if use_sn else None
         self._lazy_src = (xd, snd, idx32, k, epoch)
         self._x_aug, self._first_pn_out = None, None
-        fpn = self.first_pointnet
-        if (fast and self.fuse_pool and M <= 256 and fpn.layers[0].fast(xd)
-                and fpn._tc_eligible(6 if use_sn else 3, None)):
+        pooled = None
+        if fused:
             # fused path: node-sorted copies -> tcgen05 PointResNet -> per-node max. Neither
             # x_augmented nor first_pn_out [B,384,kN] is materialised (they stay available as
             # lazily recomputed attributes for callers that read them).
-            xs, ns, p0 = ops.som_sort_decenter(xd, snd, self.som_node, idx32, a["count"], k)
+            if not group:
+                xs, ns, p0 = ops.som_sort_decenter(xd, snd, self.som_node, idx32, a["count"], k)
             blob, fpar = fpn._tc_params()
-            self.first_pn_out_masked_max = ops.pointresnet_tc_pool(xs, blob, fpar, ns, p0, M)
+            pooled = ops.pointresnet_tc_pool(xs, blob, fpar, ns, p0, M, finalize=False)
+            done = None
+            if opt.som_k >= 2:   # pool_finalize folds into the KNN module's input assembly
+                done = self.knnlayer.forward_pooled(self.som_node, pooled, node_knn_I, opt.som_k,
+                                                    opt.som_k_type, epoch)
+            if done is None:
+                self.first_pn_out_masked_max = ops.pool_finalize(*pooled)
+                pooled = None
+            else:
+                self.knn_center_1, self.knn_feature_1, self.first_pn_out_masked_max = done
         elif fast:
             x_aug, _ = ops.som_decenter(xd, snd, self.som_node, idx32, k)
             self._x_aug = x_aug
@@ -192,9 +208,10 @@ class Encoder(nn.Module):
                 dim=2, index=gather_index * mask_row_max.unsqueeze(1).long())
 
         if opt.som_k >= 2:
-            self.knn_center_1, self.knn_feature_1 = self.knnlayer(
-                self.som_node, self.first_pn_out_masked_max, node_knn_I, opt.som_k, opt.som_k_type,
-                epoch)
+            if pooled is None:
+                self.knn_center_1, self.knn_feature_1 = self.knnlayer(
+                    self.som_node, self.first_pn_out_masked_max, node_knn_I, opt.som_k,
+                    opt.som_k_type, epoch)
             self.final_pn_out = self.final_pointnet.forward_pair(self.knn_center_1,
                                                                  self.knn_feature_1, epoch)
         else:

@@ -32,10 +32,10 @@ def _stream(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
-def _call(name, *args):
+def _call(name, *args, kernels=None):
     global LAUNCHES, KERNEL_LAUNCHES
     LAUNCHES += 1
-    KERNEL_LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
+    KERNEL_LAUNCHES += _KERNELS_PER_CALL.get(name, 1) if kernels is None else kernels
     if PROFILE is None:
         _C.check(getattr(_C.lib(), name)(*args), name)
         return
@@ -85,7 +85,8 @@ def som_assign(x, node, k, want_i64=False, want_stats=True):
             count = torch.empty((B, M), dtype=torch.int32, device=dev)
             cmean = torch.empty((B, 3, M), dtype=torch.float32, device=dev)
         _call("sonet_som_assign", _C.ptr(x), _C.ptr(node), B, N, M, int(k), _C.ptr(idx32),
-              _C.ptr(idx64), _C.ptr(count), _C.ptr(row_max), _C.ptr(cmean), _stream(x))
+              _C.ptr(idx64), _C.ptr(count), _C.ptr(row_max), _C.ptr(cmean), _stream(x),
+              kernels=2 if want_stats else 1)
     return dict(min_idx_i32=idx32, min_idx_i64=idx64, count=count, row_max=row_max,
                 cluster_mean=cmean)
 
@@ -345,11 +346,75 @@ def som_sort_decenter(x, sn, cluster_mean, min_idx_i32, count, k):
     return xs, ns, p0
 
 
+_MAX_SMEM = {}
+
+
+def som_group_fits(N, M, k, dev):
+    """Does sonet_som_group_decenter's per-cloud shared-memory footprint fit on this device?"""
+    cap = _MAX_SMEM.get(dev)
+    if cap is None:
+        cap = _MAX_SMEM[dev] = torch.cuda.get_device_properties(dev).shared_memory_per_block_optin
+    return N < (1 << 24) and M <= 256 and \
+        _C.lib().sonet_som_group_smem_bytes(int(N), int(M), int(k)) <= cap
+
+
+def som_group_decenter(x, sn, min_idx_i32, M, k):
+    """Cluster statistics + stable node sort + decentring in one launch (classifier path).
+    -> (x_sorted [B,3(+3),kN], node_sorted [B,kN] i32, pos0 [B] i32, count [B,M] i32,
+    cluster_mean [B,3,M])."""
+    _chk(x, "x", torch.float32)
+    _chk(sn, "sn", torch.float32, optional=True)
+    _chk(min_idx_i32, "min_idx", torch.int32)
+    B, _, N = x.shape
+    kN = k * N
+    dev = x.device
+    with torch.cuda.device(dev):
+        xs = torch.empty((B, 6 if sn is not None else 3, kN), dtype=torch.float32, device=dev)
+        ns = torch.empty((B, kN), dtype=torch.int32, device=dev)
+        p0 = torch.empty((B,), dtype=torch.int32, device=dev)
+        count = torch.empty((B, M), dtype=torch.int32, device=dev)
+        cmean = torch.empty((B, 3, M), dtype=torch.float32, device=dev)
+        _call("sonet_som_group_decenter", _C.ptr(x), _C.ptr(sn), _C.ptr(min_idx_i32), B, N, int(M),
+              int(k), _C.ptr(count), _C.ptr(cmean), _C.ptr(xs), _C.ptr(ns), _C.ptr(p0), _stream(x))
+    return xs, ns, p0, count, cmean
+
+
 _POOL_KEYS = {}   # (device, B, M) -> persistent key buffer (self-resetting: finalize re-inits it)
 
 
-def pointresnet_tc_pool(x_sorted, blob, fparams, node_sorted, pos0, M):
-    """Fused tcgen05 PointResNet + per-node max: -> first_pn_out_masked_max [B,384,M]."""
+def pool_finalize(keys, p0):
+    """Pool keys [B,C,M] i32 + copy-0 features [B,C] -> first_pn_out_masked_max [B,C,M]; resets
+    the keys."""
+    B, C, M = keys.shape
+    with torch.cuda.device(keys.device):
+        out = torch.empty((B, C, M), dtype=torch.float32, device=keys.device)
+        _call("sonet_pool_finalize", _C.ptr(keys), _C.ptr(p0), B, C, M, _C.ptr(out), _stream(keys))
+    return out
+
+
+def knn_assemble_pool(coord, keys, p0, idx, K, center_type):
+    """knn_assemble reading the per-node maxima from the pool keys (pool_finalize folded in).
+    -> (center [B,3,M], x_aug [B,3+C,M*K], masked_max [B,C,M])."""
+    _chk(coord, "coordinate", torch.float32)
+    _chk(keys, "pool_keys", torch.int32)
+    _chk(p0, "p0", torch.float32)
+    _chk(idx, "knn_I", torch.int64)
+    B, C, M = keys.shape
+    Kstride = idx.shape[2]
+    ct = {"avg": 0, "center": 1}[center_type]
+    dev = keys.device
+    with torch.cuda.device(dev):
+        center = torch.empty((B, 3, M), dtype=torch.float32, device=dev)
+        x_aug = torch.empty((B, 3 + C, M * K), dtype=torch.float32, device=dev)
+        mm = torch.empty((B, C, M), dtype=torch.float32, device=dev)
+        _call("sonet_knn_assemble_pool_f32", _C.ptr(coord), _C.ptr(keys), _C.ptr(p0), _C.ptr(idx), B,
+              C, M, int(K), Kstride, ct, _C.ptr(mm), _C.ptr(center), _C.ptr(x_aug), _stream(keys))
+    return center, x_aug, mm
+
+
+def pointresnet_tc_pool(x_sorted, blob, fparams, node_sorted, pos0, M, finalize=True):
+    """Fused tcgen05 PointResNet + per-node max: -> first_pn_out_masked_max [B,384,M], or with
+    finalize=False the raw (keys [B,384,M] i32, p0 [B,384]) for knn_assemble_pool / pool_finalize."""
     _chk(x_sorted, "x_sorted", torch.float32)
     _chk(blob, "blob", torch.uint8)
     _chk(fparams, "fparams", torch.float32)
@@ -365,13 +430,12 @@ def pointresnet_tc_pool(x_sorted, blob, fparams, node_sorted, pos0, M):
             _call("sonet_pool_keys_init", _C.ptr(keys), keys.numel(), _stream(x_sorted))
             _POOL_KEYS[kk] = keys
         p0 = torch.empty((B, 384), dtype=torch.float32, device=dev)
-        out = torch.empty((B, 384, M), dtype=torch.float32, device=dev)
         _call("sonet_pointresnet_tc_pool_forward", _C.ptr(x_sorted), Cin, B, P, _C.ptr(blob),
               _C.ptr(fparams), _C.ptr(node_sorted), _C.ptr(pos0), int(M), _C.ptr(keys), _C.ptr(p0),
               _stream(x_sorted))
-        _call("sonet_pool_finalize", _C.ptr(keys), _C.ptr(p0), B, 384, int(M), _C.ptr(out),
-              _stream(x_sorted))
-    return out
+    if not finalize:
+        return keys, p0
+    return pool_finalize(keys, p0)
 
 
 def som_query_topk(x, node, k):

@@ -274,3 +274,63 @@ def test_chamfer_golden_and_properties():
     p = torch.randperm(777, device=DEV)
     r2 = ops.chamfer(x[:, :, p].contiguous(), x, want_idx=False)
     assert_close(r2["loss"][2], 2e-4, "permuted self chamfer", 1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N,M,k,use_sn,mode", [(3, 1000, 64, 3, True, "sampled"),
+                                                  (2, 777, 64, 3, False, "uniform"),
+                                                  (2, 5000, 64, 3, True, "sampled"),
+                                                  (2, 130, 16, 2, True, "sampled")])
+def test_som_group_decenter_matches_two_kernel_path(B, N, M, k, use_sn, mode):
+    """sonet_som_group_decenter (statistics + stable sort + decentre, one launch) against
+    sonet_som_assign's statistics + a torch stable sort: counts equal, means within fp32 sum
+    reordering, rows in ascending stacked order inside every node, decentring bit-exact given
+    the kernel's own means, pos0 = sorted position of stacked copy 0; repeatable bit for bit."""
+    from sonet_b200 import ops, synth
+    inp = synth.synth_inputs(B, N, M, seed=N, node_mode=mode)
+    x, sn, node = inp["pc"].to(DEV), inp["sn"].to(DEV), inp["node"].to(DEV)
+    if mode == "uniform":
+        node[:, :, 2:5] += 40.0                      # empty nodes
+    a = ops.som_assign(x, node, k)
+    idx = a["min_idx_i32"]
+    xs, ns, p0, count, cmean = ops.som_group_decenter(x, sn if use_sn else None, idx, M, k)
+    xs2, ns2, p02, count2, cmean2 = ops.som_group_decenter(x, sn if use_sn else None, idx, M, k)
+    for u, v in ((xs, xs2), (ns, ns2), (p0, p02), (count, count2), (cmean, cmean2)):
+        assert torch.equal(u, v)
+    assert torch.equal(count, a["count"])
+    assert_close(cmean, a["cluster_mean"], "cluster_mean", tol=1e-5)
+    order = torch.argsort(idx.long(), dim=1, stable=True)             # [B,kN]
+    assert torch.equal(ns.long(), torch.gather(idx.long(), 1, order))
+    n_of = order % N
+    x_g = torch.gather(x, 2, n_of.unsqueeze(1).expand(-1, 3, -1))
+    ctr = torch.gather(cmean, 2, ns.long().unsqueeze(1).expand(-1, 3, -1))
+    assert torch.equal(xs[:, 0:3], x_g - ctr)
+    if use_sn:
+        assert torch.equal(xs[:, 3:6], torch.gather(sn, 2, n_of.unsqueeze(1).expand(-1, 3, -1)))
+    assert torch.equal(p0.long(), (order == 0).long().argmax(dim=1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("center_type", ["avg", "center"])
+def test_knn_assemble_pool_equals_finalize_then_assemble(center_type):
+    """sonet_knn_assemble_pool_f32 == sonet_pool_finalize + sonet_knn_assemble_f32, bit for bit,
+    incl. untouched keys (empty node -> copy-0 feature), values <= -1000, and the key reset."""
+    from sonet_b200 import ops
+    B, C, M, K = 3, 37, 64, 9
+    g = torch.Generator().manual_seed(7)
+    vals = torch.randn(B, C, M, generator=g) * 3
+    vals[0, :, 5] = -2000.0                                           # fails the > -1000 test
+    bits = vals.view(torch.int32)
+    keys = (bits ^ ((bits >> 31) & 0x7fffffff)).to(DEV)
+    keys[1, :, 7] = -2 ** 31                                          # never written: empty node
+    p0 = torch.randn(B, C, generator=g).to(DEV)
+    coord = torch.randn(B, 3, M, generator=g).to(DEV)
+    idx = torch.randint(0, M, (B, M, K + 2), generator=g).to(DEV)
+    k1, k2 = keys.clone(), keys.clone()
+    want_mm = ops.pool_finalize(k1, p0)
+    want_center, want_x = ops.knn_assemble(coord, want_mm, idx, K, center_type)
+    center, x_aug, mm = ops.knn_assemble_pool(coord, k2, p0, idx, K, center_type)
+    assert torch.equal(mm, want_mm) and torch.equal(center, want_center)
+    assert torch.equal(x_aug, want_x)
+    assert bool((k2 == -2 ** 31).all()) and bool((k1 == -2 ** 31).all())
+    assert torch.equal(want_mm[0, :, 5], p0[0]) and torch.equal(want_mm[1, :, 7], p0[1])

@@ -256,7 +256,7 @@ def test_cuda_graph_replay_matches_eager_and_tracks_changes():
             m.set_input(*[inp[k] for k in keys])
             k0 = ops.KERNEL_LAUNCHES
             m.test_model()
-            assert ops.KERNEL_LAUNCHES - k0 >= 15
+            assert ops.KERNEL_LAUNCHES - k0 >= 12
             assert torch.equal(m.score, w), rep
     with torch.no_grad():
         m.classifier.fc3.linear.bias.add_(1.0)  # parameter version changes -> re-capture

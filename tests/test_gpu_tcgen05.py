@@ -198,5 +198,7 @@ def test_encoder_fused_and_lazy_attributes(monkeypatch):
     assert lazy.shape == (4, 384, 1536) and m.encoder.x_decentered.shape == (4, 3, 1536)
     m.encoder.fuse_pool = False
     m.test_model()
-    assert torch.equal(m.encoder.first_pn_out, lazy)
-    assert_close(fused, m.score, "fused vs unfused scores", 1e-6)
+    # the fused path sums the cluster means in sorted-row order (som_group_kernel), the unfused one
+    # in stacked order (som_stats_kernel): both fixed, equal to fp32 rounding of a 5000-term sum
+    assert_close(m.encoder.first_pn_out, lazy, "lazy vs materialised first_pn_out", 1e-5)
+    assert_close(fused, m.score, "fused vs unfused scores", 1e-5)
