@@ -306,8 +306,11 @@ def main():
     # ---- (1) device-resident arm -------------------------------------------------------------------
     model.set_input(*host)
     torch.cuda.synchronize()
+    # rank 0 only: eight nvidia-smi pollers hitting the driver while every timed step contains a
+    # cross-rank all-gather turn one rank's stall into everybody's
     sampler = ClockSampler(dev.index)
-    sampler.start()                                        # runs through both timed regions
+    if rank == 0:
+        sampler.start()                                    # runs through both timed regions
     for _ in range(args.warmup):
         gpu_step()
     time.sleep(0.3)                                        # let nvidia-smi deliver its first sample
