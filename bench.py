@@ -45,7 +45,9 @@ WORKLOAD = ("ModelNet40 classifier forward, batch=%d/GPU, N=%d pts, 8x8 SOM, k=%
             "fp32, eval (BASELINE.json configs[1])" % (B_PER_GPU, NPTS, K_NN, SOM_K))
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at this workload, from the committed
 # `ncu --set full` captures (profiles/r01_summary.md); None until a capture exists.
-NCU_TRAFFIC = {"index_max_f32": 1.4871e9}
+NCU_TRAFFIC = {"index_max_f32": 1.4871e9,
+               # profiles/r01h_pointresnet_tc_pool_compact.ncu-rep: 33.89 MB read + 2.8 KB written
+               "pointresnet_tc_pool_forward": 33.895e6}
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 

@@ -57,7 +57,7 @@ constexpr int BLOB_BYTES =
     W1_BYTES + L2_STAGES * L2_STAGE_BYTES + L3_CHUNKS * L3_KSTAGES * L3_STAGE_BYTES;  // 655360
 constexpr int NFP = C0 * 6 + C0 + C1 + C2 + C3 + 4;   // W0 | shift0..3 | 1/wscale1..3 (floats)
 constexpr int NUM_THREADS = 384;
-constexpr int NBAR = 2 * NSLOT + 3 + 4 + 4 + 4 + 1;
+constexpr int NBAR = 2 * NSLOT + 3 + 4 + 4 + 4 + 2;
 // shared memory carve-up
 constexpr int OFF_W1 = 0;
 constexpr int OFF_RING = OFF_W1 + W1_BYTES;
@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
   uint64_t* d3full = b_act2q + 4;          // [2]
   uint64_t* d3empty = d3full + 2;          // [2]
   uint64_t* w1_full = d3empty + 2;
+  uint64_t* b_a0free = w1_full + 1;        // MMA -> epilogue: act0 of this tile is no longer read
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
 
   // warp index through a shuffle: tells ptxas it is warp-uniform, so the role branches below are
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
       mbar_init(&d3empty[i], 8);
     }
     mbar_init(w1_full, 1);
+    mbar_init(b_a0free, 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -284,6 +286,8 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
           const uint32_t a0 = tm + (kc == 0 ? COL_A0 : COL_D2 + 64 * (kc - 1));
           tc::mma_ts_stage<4>(d, a0, bdesc(sb, 1024), bdesc(sb + L3_STAGE_BYTES / 2, 1024), ID3,
                               kc != 0);
+          // the last chunk's first K stage is the tile's last reader of act0
+          if (nc == L3_CHUNKS - 1 && kc == 0) tc::commit_elect(b_a0free);
           release_slot();
           next_slot();
         }
@@ -407,14 +411,16 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
     uint32_t v0[16], v1[16], v2[16];    // this warp's 48 accumulator columns of one chunk
     bool parked = false;                // v0..v2 hold the previous tile's last chunk
     if (my_tiles > 0) prefetch_x(0);
-    // Iteration t: layer 0 .. layer-2 epilogue of tile t, then the chunk steps. Step -1 finishes
-    // the chunk parked by tile t-1 (its pooling runs while chunk 0's MMAs execute), steps 0..3 read
-    // chunk nc out of TMEM, release the buffer and finish it at once — except the last chunk,
-    // which stays parked so that the next tile's layer 0 starts immediately. One extra iteration
-    // drains the last parked chunk.
+    // Iteration t: layer-1/2 epilogues of tile t, then the chunk steps. Step -1 finishes the chunk
+    // parked by tile t-1 (its pooling runs while this tile's layer-2 MMAs execute) and runs the
+    // layer-2 epilogue; steps 0..3 read chunk nc out of TMEM, release the buffer and finish it at
+    // once — except the last chunk, which stays parked. Before reading the last chunk (its MMAs
+    // are still running, but act0 is free: b_a0free) the NEXT tile's layer 0 is computed, so the
+    // MMA warp can start that tile the moment the chunk has been read. Iteration -1 only computes
+    // the first tile's layer 0; iteration my_tiles only drains the last parked chunk.
 #pragma unroll 1
-    for (int t = 0; t <= my_tiles; ++t) {
-      const bool live = t < my_tiles;
+    for (int t = -1; t <= my_tiles; ++t) {
+      const bool live = t >= 0 && t < my_tiles;
       const int tile = blockIdx.x + t * gridDim.x;
       const int b = tile / tiles_per_cloud;
       const int j = (tile - b * tiles_per_cloud) * TILE + r;
@@ -422,28 +428,6 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
       const uint32_t par = t & 1;
       int nd_next = -1, p0row = -1;
       if (live) {
-        if (warp == 4) PM_TL(1, 0);
-        // ---- layer 0 on CUDA cores: 32 of the 64 channels per warpgroup, from xn[] ----
-#pragma unroll 1
-        for (int g = 0; g < 2; ++g) {
-          const int ch0 = 32 * h + 16 * g;
-          float y[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float* w = W0 + (ch0 + i) * 6;
-            float a = sh0[ch0 + i];
-#pragma unroll
-            for (int c = 0; c < 6; ++c) a = fmaf(w[c], xn[c], a);
-            y[i] = fminf(fmaxf(a, 0.f), 65504.f);
-          }
-          uint32_t wds[16];
-          tc::split16_f16(y, wds);
-          tc::st16(lane_base + COL_A0 + ch0, wds);
-        }
-        tc::wait_st();
-        tc::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(b_act0);
         if (warp == 4) PM_TL(1, 1);
         // this tile's node ids / copy-0 row: their L2 latency hides behind layers 1-2
         if (POOL) {
@@ -478,9 +462,39 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
       }
 
       // ---- layer 3 epilogue: four chunks of 96 channels, 48 per warpgroup; bare layer (no ReLU) ----
-      const int nc_end = live ? L3_CHUNKS : 0;
+      const int nc_begin = (t < 0) ? L3_CHUNKS - 1 : -1;
+      const int nc_end = (live || t < 0) ? L3_CHUNKS : 0;
 #pragma unroll 1
-      for (int nc = -1; nc < nc_end; ++nc) {
+      for (int nc = nc_begin; nc < nc_end; ++nc) {
+        if (nc == L3_CHUNKS - 1 && t + 1 < my_tiles) {
+          // ---- layer 0 of tile t+1 on CUDA cores (32 of the 64 channels per warpgroup, from the
+          // prefetched xn[]), as soon as tile t's MMAs no longer read act0 ----
+          if (t >= 0) {
+            tc::mbar_wait_bounded(b_a0free, par, 23);
+            tc::fence_after_sync();
+          }
+          if (warp == 4) PM_TL(1, 0);
+#pragma unroll 1
+          for (int g = 0; g < 2; ++g) {
+            const int ch0 = 32 * h + 16 * g;
+            float y[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float* w = W0 + (ch0 + i) * 6;
+              float a = sh0[ch0 + i];
+#pragma unroll
+              for (int c = 0; c < 6; ++c) a = fmaf(w[c], xn[c], a);
+              y[i] = fminf(fmaxf(a, 0.f), 65504.f);
+            }
+            uint32_t wds[16];
+            tc::split16_f16(y, wds);
+            tc::st16(lane_base + COL_A0 + ch0, wds);
+          }
+          tc::wait_st();
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b_act0);
+        }
         if (nc == 0) {                  // from here on the chunks belong to tile t
           cx_b = b;
           cx_valid = valid;
@@ -492,7 +506,7 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
             cx_any_p0 = __any_sync(FULL, cx_is_p0);
           }
         }
-        if (nc >= 0) {
+        if (nc >= 0 && t >= 0) {
           const int buf = nc & 1;
           tc::mbar_wait_bounded(&d3full[buf], (nc >> 1) & 1, 22);   // two uses per tile: parity = use&1
           tc::fence_after_sync();

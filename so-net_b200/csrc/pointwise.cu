@@ -216,6 +216,34 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- row max, L = 4*G with G a power of two <= 32: G lanes per row, one 128-bit load per lane,
+// four row groups in flight per warp ----
+__global__ void __launch_bounds__(256)
+    rowmax_vec_kernel(const float4* __restrict__ in, long long R, int G, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int rpw = 32 / G;                       // rows per warp and pass
+  const int sub = lane / G;
+  const long long row0 = warp_id * (4LL * rpw) + sub;
+  float m[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const long long r = row0 + static_cast<long long>(u) * rpw;
+    if (r < R) {
+      const float4 v = __ldg(in + r * G + (lane - sub * G));
+      m[u] = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+    } else {
+      m[u] = -__int_as_float(0x7f800000);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    for (int o = G >> 1; o > 0; o >>= 1) m[u] = fmaxf(m[u], __shfl_xor_sync(0xffffffffu, m[u], o));
+    const long long r = row0 + static_cast<long long>(u) * rpw;
+    if (lane == sub * G && r < R) out[r] = m[u];
+  }
+}
+
 // ---- row max: in [R, L] -> out [R] --------------------------------------------------------------------
 // L <= 32: one thread per row group (lanes cover consecutive rows); else one warp per row.
 __global__ void __launch_bounds__(256)
@@ -483,7 +511,12 @@ extern "C" int sonet_rowmax_f32(const float* in, int R, int L, float* out, sonet
   SONET_REQUIRE(R >= 0 && L >= 1, "rowmax: bad dimension");
   if (R == 0) return SONET_OK;
   SONET_REQUIRE(in && out, "rowmax: null pointer");
-  if (L <= 32) {
+  const int G = L / 4;
+  if (L % 4 == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0 && L > 32 && aligned16(in)) {
+    const long long warps = (static_cast<long long>(R) + 4 * (32 / G) - 1) / (4 * (32 / G));
+    rowmax_vec_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(in), R, G, out);
+  } else if (L <= 32) {
     rowmax_small_kernel<<<(R + 255) / 256, 256, 0, as_stream(stream)>>>(in, R, L, out);
   } else {
     const long long threads = static_cast<long long>(R) * 32;

@@ -200,8 +200,14 @@ def test_linear_rowmax_kcopy():
     shift = torch.from_numpy(rs.normal(size=40).astype(np.float32))
     want = F.relu(F.linear(x, W) + shift)
     assert_close(ops.linear(x.to(DEV), W.to(DEV), None, shift.to(DEV), True), want, "linear", 2e-5)
-    t = torch.from_numpy(rs.normal(size=(3, 7, 64)).astype(np.float32))
-    assert torch.equal(ops.rowmax(t.to(DEV)).cpu(), t.max(dim=2)[0])
+    # rows are independent: a sub-batch gives the same bits
+    xb = torch.from_numpy(rs.normal(size=(67, 1024)).astype(np.float32)).to(DEV)
+    full = ops.linear(xb, W.to(DEV), None, shift.to(DEV), False)
+    assert torch.equal(ops.linear(xb[:3].contiguous(), W.to(DEV), None, shift.to(DEV), False), full[:3])
+    assert_close(full.cpu(), F.linear(xb.cpu(), W) + shift, "linear B=67", 2e-5)
+    for shape in ((3, 7, 64), (5, 3, 128), (2, 1033, 64), (2, 3, 40), (3, 5, 16)):
+        t = torch.from_numpy(rs.normal(size=shape).astype(np.float32))
+        assert torch.equal(ops.rowmax(t.to(DEV)).cpu(), t.max(dim=2)[0]), shape
     t = torch.from_numpy(rs.normal(size=(2, 6, 5, 9)).astype(np.float32))
     assert torch.equal(ops.rowmax(t.to(DEV)).cpu(), t.max(dim=3)[0])
     t = torch.from_numpy(rs.normal(size=(2, 4, 300)).astype(np.float32))
