@@ -20,8 +20,9 @@ PY
 if [ "${NCU:-1}" = "1" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv \
    --log-file gpurun_out/launches_$TAG.csv python tools/profile_step.py --steps 4 > gpurun_out/ncu_list_$TAG.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:index_max -s 2 -c 1 \
-   -o gpurun_out/prof_index_max_$TAG -f python tools/profile_step.py --steps 3 > gpurun_out/ncu_im_$TAG.log 2>&1
+# index_max is a standalone API op (not in the classifier step): bench.py's standalone section launches it
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:index_max -s 1 -c 1 \
+   -o gpurun_out/prof_index_max_$TAG -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_im_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:pointresnet_tc -s 2 -c 1 \
    -o gpurun_out/prof_pointresnet_tc_$TAG -f python tools/profile_step.py --steps 3 > gpurun_out/ncu_tc_$TAG.log 2>&1
 tail -3 gpurun_out/ncu_tc_$TAG.log
