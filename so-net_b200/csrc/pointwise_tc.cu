@@ -15,7 +15,10 @@
 //     warp instruction whatever its width, and at 4 B the 256 instructions of a chunk took longer
 //     than its MMAs — then clamp to the fp16 range, split into fp16 hi/lo and write the K-major
 //     no-swizzle A images with one 128-bit shared store per 8 channels (conflict free),
-//     fence.proxy.async, arrive;
+//     fence.proxy.async, arrive. When P % 64 == 0 and the layer has one source tensor, the chunk
+//     is fetched by TENSOR-MAP TMA instead: a 128-row tile is exactly two [64 p x 64 c] boxes of a
+//     3-D map over x[B][C][P] (out-of-range channels / clouds are zero-filled by the hardware), two
+//     instructions per chunk instead of 64 LDGSTS whose outstanding-request limit set the pace;
 //   * TMA warp: streams the pre-packed fp16 hi/lo weight images (cp.async.bulk + mbarrier);
 //   * MMA warp (one thread): 3 tcgen05.mma.kind::f16 per 16-channel K step (hi*hi + lo*hi + hi*lo),
 //     SS mode, M=128, N<=256, fp32 accumulation in TMEM, two 256-column accumulator buffers so the
@@ -24,7 +27,10 @@
 //     lane = row => 128-byte coalesced along p.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 
 #include "tc_common.cuh"
 
@@ -40,7 +46,7 @@ constexpr int OFF_W = OFF_A + NSTAGE * A_BYTES;
 constexpr int OFF_STG = OFF_W + NSTAGE * W_BYTES;   // fp32 staging of one activation chunk
 constexpr int STG_BYTES = KCH * TILE * 4;            // [64 ch][128 rows] fp32, 32 KB
 constexpr int OFF_BAR = OFF_STG + STG_BYTES;
-constexpr int NBAR = 3 * NSTAGE + 4;
+constexpr int NBAR = 3 * NSTAGE + 5;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 
@@ -50,6 +56,7 @@ struct Dims {
   int ntiles;    // out-channel tiles of <= 256 (each a multiple of 64)
   int cin_pad;   // Cin rounded up to 16
   int vec4;      // 16-byte activation fetch is legal (P % 4 == 0, 16-byte aligned bases)
+  int tma;       // activation chunks by tensor-map TMA (single source, P % 64 == 0)
   float inv;     // 1 / weight pre-scale
 };
 __host__ __device__ inline int ntile_width(int Cout, int nt) {
@@ -62,7 +69,8 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
     pointwise_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
                         const unsigned char* __restrict__ blob, const float* __restrict__ shift,
                         const float* __restrict__ addend, const int32_t* __restrict__ gidx,
-                        float* __restrict__ out, pwt::Dims d, long long* __restrict__ dbg) {
+                        float* __restrict__ out, pwt::Dims d, long long* __restrict__ dbg,
+                        const __grid_constant__ CUtensorMap xmap) {
   using namespace pwt;
 #define PW_TL(role, idx)                                                   \
   do {                                                                     \
@@ -77,6 +85,7 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
   uint64_t* empty = bars + 2 * NSTAGE;      // [NSTAGE] MMA -> TMA + converters
   uint64_t* d_full = bars + 3 * NSTAGE;     // [2] MMA -> epilogue
   uint64_t* d_empty = d_full + 2;           // [2] epilogue -> MMA
+  uint64_t* stg_full = d_empty + 2;         // TMA -> converters (staging tile landed)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
 
   // warp index through a shuffle: ptxas then knows the role branches are warp-uniform
@@ -99,6 +108,7 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
       mbar_init(&d_full[i], 1);
       mbar_init(&d_empty[i], 8);
     }
+    mbar_init(stg_full, 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -186,6 +196,26 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
       const int it = qq / d.kchunks, kc = qq - it * d.kchunks;
       const int item = blockIdx.x + it * gridDim.x;
       const long long R0 = static_cast<long long>(item / d.ntiles) * TILE;
+      if (d.tma) {
+        // two [64 p][64 c] boxes; staging layout [box][c][64 p]. Rows past the last cloud give
+        // b >= B (fully out of range): the box is zero-filled and still counts its bytes.
+        if (t == 0) {
+          mbar_arrive_expect_tx(stg_full, STG_BYTES);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const long long R = R0 + 64 * i;
+            const int b = static_cast<int>(R / d.P);
+            const int p = static_cast<int>(R - static_cast<long long>(b) * d.P);
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+                "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(smem + OFF_STG) + i * (STG_BYTES / 2)),
+                "l"(reinterpret_cast<uint64_t>(&xmap)), "r"(p), "r"(kc * KCH), "r"(b),
+                "r"(smem_u32(stg_full))
+                : "memory");
+          }
+        }
+        return;
+      }
       if (d.vec4) {
         // warp w copies channels w, w+8, ..., w+56 of the chunk; lane l the rows 4l..4l+3 (never
         // across a cloud boundary because P % 4 == 0)
@@ -236,11 +266,19 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
     auto conv_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     if (total > 0) issue(0);
     for (uint32_t qq = 0; qq < total; ++qq) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      conv_sync();                          // every thread's copies have landed
       float v[32];
+      if (d.tma) {
+        tc::mbar_wait_bounded(stg_full, qq & 1, 206);   // both boxes have landed
+        const float* sb = reinterpret_cast<const float*>(smem + OFF_STG) + (m >> 6) * (KCH * 64) +
+                          (half * 32) * 64 + (m & 63);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = stg[i * TILE];
+        for (int i = 0; i < 32; ++i) v[i] = sb[i * 64];
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        conv_sync();                        // every thread's copies have landed
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = stg[i * TILE];
+      }
       conv_sync();                          // the staging tile has been read: refill it
       if (qq + 1 < total) issue(qq + 1);
       const uint32_t slot = qq % NSTAGE, use = qq / NSTAGE;
@@ -390,6 +428,37 @@ extern "C" int sonet_pointwise_tc_pack(const float* W, int Cout, int Cin, void* 
   return SONET_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link against libcuda)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                      const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    cudaGetLastError();
+    return reinterpret_cast<TensorMapEncodeFn>(p);
+  }();
+  return fn;
+}
+// 3-D map over x[B][C][P] fp32, box [64 p][64 c][1]; false when the layout does not qualify
+static bool make_activation_map(CUtensorMap* m, const float* x, int B, int C, int P) {
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (enc == nullptr || P % 64 != 0 || !sonet::aligned16(x)) return false;
+  const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(P), static_cast<cuuint64_t>(C),
+                              static_cast<cuuint64_t>(B)};
+  const cuuint64_t gstr[2] = {static_cast<cuuint64_t>(P) * 4, static_cast<cuuint64_t>(C) * P * 4};
+  const cuuint32_t box[3] = {64, 64, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int launch_pointwise_tc(const float* x0, int C0, const float* x1, int C1, int B,
                                           int P, const void* blob, float inv_scale,
                                           const float* shift, int Cout, int relu,
@@ -410,6 +479,13 @@ static int launch_pointwise_tc(const float* x0, int C0, const float* x1, int C1,
   d.ntiles = ((Cout + 63) / 64 * 64 + NT - 1) / NT;
   d.inv = inv_scale;
   d.vec4 = (P % 4 == 0) && aligned16(x0) && (C1 == 0 || aligned16(x1));
+  CUtensorMap xmap;
+  std::memset(&xmap, 0, sizeof(xmap));
+  static const bool tma_off = [] {
+    const char* e = getenv("SONET_PW_TMA");
+    return e != nullptr && e[0] == '0';
+  }();
+  d.tma = (!tma_off && C1 == 0 && make_activation_map(&xmap, x0, B, C0, P)) ? 1 : 0;
   const long long rows = static_cast<long long>(B) * P;
   const long long items = (rows + TILE - 1) / TILE * d.ntiles;
   SONET_REQUIRE(items < (1LL << 31), "pointwise_tc: too many tiles");
@@ -417,7 +493,7 @@ static int launch_pointwise_tc(const float* x0, int C0, const float* x1, int C1,
   cudaFuncSetAttribute(pointwise_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   const int grid = static_cast<int>(std::min<long long>(items, sm_count()));
   pointwise_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, as_stream(stream)>>>(
-      x0, x1, static_cast<const unsigned char*>(blob), shift, addend, gidx, out, d, dbg);
+      x0, x1, static_cast<const unsigned char*>(blob), shift, addend, gidx, out, d, dbg, xmap);
   return check_launch("pointwise_tc");
 }
 
