@@ -8,7 +8,10 @@
 //   out[b,co,p] = act( inv * sum_ci Ws[co,ci] * X[b,ci,p] + shift[co] (+ addend[b,co,g(b,p)]) )
 //
 // Rows (b,p) are flattened and tiled by 128 = MMA M = TMEM lanes; an item is (row tile, 256-wide
-// out-channel tile); K streams in 64-channel chunks through a 2-stage ring:
+// out-channel tile); K streams in 64-channel activation chunks (2-stage ring of converted A images,
+// two fp32 staging tiles ahead of it) and 32-channel weight stages (3-stage ring; the small weight
+// stage is what leaves room for the second staging tile — with one, fetch and conversion of a
+// chunk were serial and ncu showed the kernel latency-bound at 12 % DRAM / 38 % tensor pipe):
 //   * converter warps (8): fetch the fp32 activations with cp.async into a staging buffer — 16 B
 //     per thread (4 consecutive rows of one channel: a warp instruction moves one channel's 128
 //     rows) when P and the base pointers allow it, 4 B otherwise; LDGSTS costs ~8 LSU cycles per
@@ -37,16 +40,20 @@
 namespace sonet {
 namespace pwt {
 constexpr int TILE = 128, KCH = 64, NT = 256;
+constexpr int WK = 32;                         // K extent of one weight stage (two per A chunk)
 constexpr int A_BYTES = 2 * TILE * KCH * 2;   // hi + lo images of the activation chunk, 32 KB
-constexpr int W_BYTES = 2 * NT * KCH * 2;     // hi + lo images of the weight chunk, 64 KB
-constexpr int NSTAGE = 2;
+constexpr int W_BYTES = 2 * NT * KCH * 2;     // hi + lo weight images of one (n-tile, 64-k chunk) in the blob
+constexpr int WS_BYTES = 2 * NT * WK * 2;     // one weight stage in shared memory, 32 KB
+constexpr int NSTAGE = 2;                      // A ring
+constexpr int NSTAGE_W = 3;                    // weight ring
+constexpr int NSTG = 2;                        // fp32 staging tiles (TMA fetch runs two chunks ahead)
 constexpr int NUM_THREADS = 640;   // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 4-11 epilogue, 12-19 converters
 constexpr int OFF_A = 0;
 constexpr int OFF_W = OFF_A + NSTAGE * A_BYTES;
-constexpr int OFF_STG = OFF_W + NSTAGE * W_BYTES;   // fp32 staging of one activation chunk
-constexpr int STG_BYTES = KCH * TILE * 4;            // [64 ch][128 rows] fp32, 32 KB
-constexpr int OFF_BAR = OFF_STG + STG_BYTES;
-constexpr int NBAR = 3 * NSTAGE + 5;
+constexpr int OFF_STG = OFF_W + NSTAGE_W * WS_BYTES;   // fp32 staging of activation chunks
+constexpr int STG_BYTES = KCH * TILE * 4;               // [64 ch][128 rows] fp32, 32 KB
+constexpr int OFF_BAR = OFF_STG + NSTG * STG_BYTES;
+constexpr int NBAR = 2 * NSTAGE_W + 2 * NSTAGE + 4 + NSTG;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 
@@ -80,12 +87,13 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
   if (dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) dbg[127] = clock64();
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* full_w = bars;                  // [NSTAGE] TMA -> MMA
-  uint64_t* full_a = bars + NSTAGE;         // [NSTAGE] converters -> MMA
-  uint64_t* empty = bars + 2 * NSTAGE;      // [NSTAGE] MMA -> TMA + converters
-  uint64_t* d_full = bars + 3 * NSTAGE;     // [2] MMA -> epilogue
-  uint64_t* d_empty = d_full + 2;           // [2] epilogue -> MMA
-  uint64_t* stg_full = d_empty + 2;         // TMA -> converters (staging tile landed)
+  uint64_t* full_w = bars;                        // [NSTAGE_W] TMA -> MMA
+  uint64_t* empty_w = full_w + NSTAGE_W;          // [NSTAGE_W] MMA -> TMA
+  uint64_t* full_a = empty_w + NSTAGE_W;          // [NSTAGE] converters -> MMA
+  uint64_t* empty_a = full_a + NSTAGE;            // [NSTAGE] MMA -> converters
+  uint64_t* d_full = empty_a + NSTAGE;            // [2] MMA -> epilogue
+  uint64_t* d_empty = d_full + 2;                 // [2] epilogue -> MMA
+  uint64_t* stg_full = d_empty + 2;               // [NSTG] TMA -> converters (staging tile landed)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
 
   // warp index through a shuffle: ptxas then knows the role branches are warp-uniform
@@ -99,16 +107,19 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
   const int Cin = d.C0 + d.C1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) {
+    for (int s = 0; s < NSTAGE_W; ++s) {
       mbar_init(&full_w[s], 1);
+      mbar_init(&empty_w[s], 1);
+    }
+    for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full_a[s], 8);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty_a[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&d_full[i], 1);
       mbar_init(&d_empty[i], 8);
     }
-    mbar_init(stg_full, 1);
+    for (int i = 0; i < NSTG; ++i) mbar_init(&stg_full[i], 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -129,16 +140,19 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
         const int item = blockIdx.x + it * gridDim.x;
         const int nt = item % d.ntiles;
         const int nw = ntile_width(d.Cout, nt);
-        // blob offset of n-tile nt: all previous tiles are NT wide
-        size_t off = static_cast<size_t>(nt) * d.kchunks * W_BYTES;
-        const uint32_t bytes = static_cast<uint32_t>(nw) * KCH * 4;
-        for (int kc = 0; kc < d.kchunks; ++kc, ++q) {
-          const uint32_t slot = q % NSTAGE, use = q / NSTAGE;
-          if (use > 0) tc::mbar_wait_relaxed(&empty[slot], (use - 1) & 1, 200);
-          mbar_arrive_expect_tx(&full_w[slot], bytes);
-          bulk_g2s(smem + OFF_W + slot * W_BYTES, blob + off, bytes, &full_w[slot]);
-          if (it == 0) PW_TL(0, kc);
-          off += bytes;
+        // blob: n-tile nt starts after nt full-width tiles; a 64-k chunk = two [nw x 32] stages
+        const size_t off0 = static_cast<size_t>(nt) * d.kchunks * W_BYTES;
+        const uint32_t bytes = static_cast<uint32_t>(nw) * WK * 4;
+        for (int kc = 0; kc < d.kchunks; ++kc) {
+          const int halves = (d.cin_pad - kc * KCH > WK) ? 2 : 1;   // the MMA warp agrees
+          for (int hh = 0; hh < halves; ++hh, ++q) {
+            const uint32_t slot = q % NSTAGE_W, use = q / NSTAGE_W;
+            if (use > 0) tc::mbar_wait_relaxed(&empty_w[slot], (use - 1) & 1, 200);
+            mbar_arrive_expect_tx(&full_w[slot], bytes);
+            bulk_g2s(smem + OFF_W + slot * WS_BYTES,
+                     blob + off0 + (static_cast<size_t>(kc) * 2 + hh) * bytes, bytes, &full_w[slot]);
+            if (it == 0 && hh == 0) PW_TL(0, kc);
+          }
         }
       }
     }
@@ -147,7 +161,7 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
     {
       const uint32_t a_base = static_cast<uint32_t>(__cvta_generic_to_shared(smem + OFF_A)),
                      w_base = static_cast<uint32_t>(__cvta_generic_to_shared(smem + OFF_W));
-      uint32_t q = 0;
+      uint32_t qa = 0, qw = 0;
       for (int it = 0; it < my_items; ++it) {
         const int item = blockIdx.x + it * gridDim.x;
         const int nt = item % d.ntiles;
@@ -158,23 +172,32 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
         if (use > 0) tc::mbar_wait_bounded(&d_empty[buf], (use - 1) & 1, 201);
         tc::fence_after_sync();
         const uint32_t dcol = tm + buf * NT;
-        for (int kc = 0; kc < d.kchunks; ++kc, ++q) {
-          const uint32_t slot = q % NSTAGE, par = (q / NSTAGE) & 1;
-          tc::mbar_wait_bounded(&full_w[slot], par, 202);
-          if (it == 0) PW_TL(1, 3 * kc);
-          tc::mbar_wait_bounded(&full_a[slot], par, 203);
-          tc::fence_after_sync();
+        for (int kc = 0; kc < d.kchunks; ++kc, ++qa) {
+          const uint32_t sa = qa % NSTAGE, pa = (qa / NSTAGE) & 1;
+          tc::mbar_wait_bounded(&full_a[sa], pa, 203);
           if (it == 0) PW_TL(1, 3 * kc + 1);
-          const uint32_t as = a_base + slot * A_BYTES, ws = w_base + slot * W_BYTES;
+          const uint32_t as = a_base + sa * A_BYTES;
           const int nks = min(4, (d.cin_pad - kc * KCH) / 16);
-          const uint64_t ah = tc::smem_desc(as, 128, 1024), al = tc::smem_desc(as + A_BYTES / 2, 128, 1024),
-                         bh = tc::smem_desc(ws, 128, 1024),
-                         bl = tc::smem_desc(ws + nw * KCH * 2, 128, 1024);
-          if (nks == 4) tc::mma_ss_stage<4>(dcol, ah, al, bh, bl, idesc, kc != 0);
-          else if (nks == 3) tc::mma_ss_stage<3>(dcol, ah, al, bh, bl, idesc, kc != 0);
-          else if (nks == 2) tc::mma_ss_stage<2>(dcol, ah, al, bh, bl, idesc, kc != 0);
-          else tc::mma_ss_stage<1>(dcol, ah, al, bh, bl, idesc, kc != 0);
-          tc::commit_elect(&empty[slot]);
+          const int halves = (nks > 2) ? 2 : 1;
+          for (int hh = 0; hh < halves; ++hh, ++qw) {
+            const uint32_t sw = qw % NSTAGE_W, pw = (qw / NSTAGE_W) & 1;
+            tc::mbar_wait_bounded(&full_w[sw], pw, 202);
+            tc::fence_after_sync();
+            if (it == 0 && hh == 0) PW_TL(1, 3 * kc);
+            const uint32_t ws = w_base + sw * WS_BYTES;
+            // A: [128 x 64] image, SBO 1024, this half starts 2 k-steps (512 B) in;
+            // B: [nw x 32] image, SBO 512
+            const uint64_t ah = tc::smem_desc(as + hh * 512, 128, 1024),
+                           al = tc::smem_desc(as + A_BYTES / 2 + hh * 512, 128, 1024),
+                           bh = tc::smem_desc(ws, 128, 512),
+                           bl = tc::smem_desc(ws + nw * WK * 2, 128, 512);
+            const uint32_t acc = (kc | hh) != 0;
+            const int nk = (hh == 0) ? min(nks, 2) : nks - 2;
+            if (nk == 2) tc::mma_ss_stage<2>(dcol, ah, al, bh, bl, idesc, acc);
+            else tc::mma_ss_stage<1>(dcol, ah, al, bh, bl, idesc, acc);
+            tc::commit_elect(&empty_w[sw]);
+          }
+          tc::commit_elect(&empty_a[sa]);
           if (it == 0) PW_TL(1, 3 * kc + 2);
         }
         tc::commit_elect(&d_full[buf]);
@@ -200,7 +223,9 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
         // two [64 p][64 c] boxes; staging layout [box][c][64 p]. Rows past the last cloud give
         // b >= B (fully out of range): the box is zero-filled and still counts its bytes.
         if (t == 0) {
-          mbar_arrive_expect_tx(stg_full, STG_BYTES);
+          uint64_t* sfull = &stg_full[qq % NSTG];
+          const uint32_t sdst = smem_u32(smem + OFF_STG) + (qq % NSTG) * STG_BYTES;
+          mbar_arrive_expect_tx(sfull, STG_BYTES);
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             const long long R = R0 + 64 * i;
@@ -208,9 +233,9 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
             const int p = static_cast<int>(R - static_cast<long long>(b) * d.P);
             asm volatile(
                 "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
-                "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(smem + OFF_STG) + i * (STG_BYTES / 2)),
+                "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(sdst + i * (STG_BYTES / 2)),
                 "l"(reinterpret_cast<uint64_t>(&xmap)), "r"(p), "r"(kc * KCH), "r"(b),
-                "r"(smem_u32(stg_full))
+                "r"(smem_u32(sfull))
                 : "memory");
           }
         }
@@ -264,13 +289,15 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
     };
     // the 256 converter threads exchange data through the staging tile: named barrier 1
     auto conv_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    // TMA mode runs NSTG chunks ahead (alternating staging tiles); cp.async mode one (tile 0)
     if (total > 0) issue(0);
+    if (d.tma && total > 1) issue(1);
     for (uint32_t qq = 0; qq < total; ++qq) {
       float v[32];
       if (d.tma) {
-        tc::mbar_wait_bounded(stg_full, qq & 1, 206);   // both boxes have landed
-        const float* sb = reinterpret_cast<const float*>(smem + OFF_STG) + (m >> 6) * (KCH * 64) +
-                          (half * 32) * 64 + (m & 63);
+        tc::mbar_wait_bounded(&stg_full[qq % NSTG], (qq / NSTG) & 1, 206);   // both boxes landed
+        const float* sb = reinterpret_cast<const float*>(smem + OFF_STG + (qq % NSTG) * STG_BYTES) +
+                          (m >> 6) * (KCH * 64) + (half * 32) * 64 + (m & 63);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = sb[i * 64];
       } else {
@@ -280,9 +307,13 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
         for (int i = 0; i < 32; ++i) v[i] = stg[i * TILE];
       }
       conv_sync();                          // the staging tile has been read: refill it
-      if (qq + 1 < total) issue(qq + 1);
+      if (d.tma) {
+        if (qq + NSTG < total) issue(qq + NSTG);
+      } else if (qq + 1 < total) {
+        issue(qq + 1);
+      }
       const uint32_t slot = qq % NSTAGE, use = qq / NSTAGE;
-      if (use > 0) tc::mbar_wait_bounded(&empty[slot], (use - 1) & 1, 204);
+      if (use > 0) tc::mbar_wait_bounded(&empty_a[slot], (use - 1) & 1, 204);
       if (warp == 12 && qq < 16) PW_TL(2, 2 * qq);
       unsigned char* a_hi = smem + OFF_A + slot * A_BYTES + (m >> 3) * 1024 + (m & 7) * 16;
 #pragma unroll
@@ -406,23 +437,25 @@ extern "C" int sonet_pointwise_tc_pack(const float* W, int Cout, int Cin, void* 
   for (int nt = 0; nt < ntiles; ++nt) {
     const int nw = std::min(NT, cpad - nt * NT);
     for (int kc = 0; kc < kch; ++kc) {
-      unsigned char* hi = blob + off;
-      unsigned char* lo = hi + static_cast<size_t>(nw) * KCH * 2;
-      for (int r = 0; r < nw; ++r) {
-        const int co = nt * NT + r;
-        if (co >= Cout) continue;
-        for (int k = 0; k < KCH; ++k) {
-          const int ci = kc * KCH + k;
-          if (ci >= Cin) continue;
-          const float w = W[static_cast<size_t>(co) * Cin + ci] * scale;
-          const __half h = __float2half_rn(w);
-          const __half l = __float2half_rn(w - __half2float(h));
-          const uint32_t o = (r >> 3) * 1024 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2;
-          std::memcpy(hi + o, &h, 2);
-          std::memcpy(lo + o, &l, 2);
+      for (int hh = 0; hh < 2; ++hh) {   // one shared-memory weight stage = [nw x 32] hi | lo images
+        unsigned char* hi = blob + off;
+        unsigned char* lo = hi + static_cast<size_t>(nw) * WK * 2;
+        for (int r = 0; r < nw; ++r) {
+          const int co = nt * NT + r;
+          if (co >= Cout) continue;
+          for (int k = 0; k < WK; ++k) {
+            const int ci = kc * KCH + hh * WK + k;
+            if (ci >= Cin) continue;
+            const float w = W[static_cast<size_t>(co) * Cin + ci] * scale;
+            const __half h = __float2half_rn(w);
+            const __half l = __float2half_rn(w - __half2float(h));
+            const uint32_t o = (r >> 3) * 512 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2;
+            std::memcpy(hi + o, &h, 2);
+            std::memcpy(lo + o, &l, 2);
+          }
         }
+        off += static_cast<size_t>(nw) * WK * 4;
       }
-      off += static_cast<size_t>(nw) * KCH * 4;
     }
   }
   return SONET_OK;
