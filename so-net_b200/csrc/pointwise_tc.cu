@@ -72,6 +72,10 @@ __host__ __device__ inline int ntile_width(int Cout, int nt) {
 }
 }  // namespace pwt
 
+__device__ __forceinline__ bool sonet_aligned16_dev(const void* p) {
+  return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+
 __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
     pointwise_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
                         const unsigned char* __restrict__ blob, const float* __restrict__ shift,
@@ -366,10 +370,31 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
       const int cw = nw >> 1;                      // columns per warpgroup (multiple of 32)
       const int c_lo = h * cw;
       const bool all_real = (nt * NT + nw) <= d.Cout;   // no padded output channels in this tile
+      const bool sh_vec = shift != nullptr && sonet_aligned16_dev(shift);
       for (int c0 = c_lo; c0 < c_lo + cw; c0 += 32) {
         uint32_t v0[16], v1[16];
         tc::ld16(lane_base + buf * NT + c0, v0);
         tc::ld16(lane_base + buf * NT + c0 + 16, v1);
+        // the 32 shift values of this column group: 128-bit loads issued before the TMEM-load wait.
+        // (One __ldg per output element put a dependent L1 round trip in front of every FFMA: the
+        // epilogue took 23 k cycles per item, longer than the item's MMAs.)
+        const int cg = nt * NT + c0;
+        float sh[32];
+        if (sh_vec && cg + 32 <= d.Cout) {
+          const float4* s4 = reinterpret_cast<const float4*>(shift + cg);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 t4 = __ldg(s4 + q);
+            sh[4 * q] = t4.x;
+            sh[4 * q + 1] = t4.y;
+            sh[4 * q + 2] = t4.z;
+            sh[4 * q + 3] = t4.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            sh[i] = (shift != nullptr && cg + i < d.Cout) ? __ldg(shift + cg + i) : 0.f;
+        }
         tc::wait_ld();
         if (c0 + 32 >= c_lo + cw) {   // this warp's columns are all in registers: release the buffer
           tc::fence_before_sync();
@@ -377,12 +402,11 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
           if (lane == 0) mbar_arrive(&d_empty[buf]);
         }
         if (valid) {
-          const int cg = nt * NT + c0;
           float* o = out + (static_cast<size_t>(b) * d.Cout + cg) * d.P + p;
           auto emit = [&](uint32_t raw, int i) {
             const int co = cg + i;
             if (all_real || co < d.Cout) {
-              float y = fmaf(__uint_as_float(raw), d.inv, shift ? __ldg(shift + co) : 0.f);
+              float y = fmaf(__uint_as_float(raw), d.inv, sh[i]);
               if (arow) y += __ldg(arow + static_cast<size_t>(co) * d.G);
               o[static_cast<size_t>(i) * d.P] = fmaxf(y, floor_v);
             }
