@@ -221,6 +221,16 @@ def kernel_report(profile_steps, peaks):
             row.update(bound="tensor", achieved=round(ach, 3), peak=tf, unit="TFLOP/s",
                        frac=round(ach / tf, 5), shape="[%d,%d+%d,%d]->%d" % (B, C0, C1, P, Cout),
                        note="fp32 CUDA-core path vs the bf16 tensor peak")
+        elif key.startswith("pointwise_tc_forward"):
+            # args of sonet_pointwise_tc_forward: x0, C0, x1, C1, B, P, blob, inv, shift, Cout, ...
+            C0, C1, B, P, Cout = a[1], a[3], a[4], a[5], a[9]
+            flops = 2.0 * B * P * (C0 + C1) * Cout
+            ach = flops / (ms * 1e-3) / 1e12
+            row.update(bound="tensor", achieved=round(ach, 2), peak=tf, unit="TFLOP/s",
+                       frac=round(ach / tf, 4), executed_tflops=round(3 * ach, 1),
+                       shape="[%d,%d+%d,%d]->%d" % (B, C0, C1, P, Cout),
+                       note="algorithmic flops (x3 executed: fp16 hi/lo split); the CUDA-event time of "
+                            "a 30-70 us launch includes host launch latency in this eager pass")
         elif key.startswith("pointresnet_tc_forward") or key.startswith("pointresnet_tc_pool_forward"):
             Bc, P = a[2], a[3]
             flops = 328448.0 * Bc * P          # 2 * (6*64 + 64*128 + 128*256 + 320*384)
