@@ -23,13 +23,24 @@
 //   * weights (B operand, K-major no-swizzle core-matrix images packed once by the host) stream
 //     L2 -> shared memory through a 5-slot TMA ring (cp.async.bulk + mbarrier); layer-1 weights
 //     stay resident;
-//   * MMA shapes are as wide as TMEM allows, because ONE thread issues them and the issue rate is
-//     what bounded the first version (480 N=64 MMAs per tile: measured 100 -> 60 cycles per MMA
-//     against 32 cycles of tensor work): layer 1 = 12 MMAs of N=128, layer 2 = 24 of N=256,
-//     layer 3 = 4 chunks x 60 of N=96 over two accumulator buffers (its epilogue — shift add +
-//     coalesced fp32 stores, lane = point — overlaps the next chunk's MMAs): 276 MMAs per tile;
-//   * the MMA warp stays converged and `elect.sync` predicates each tcgen05 instruction (issuing
-//     from a divergent `if (lane == 0)` makes nvcc wrap every UTCHMMA in an ELECT/BRA loop);
+//   * MMA shapes are as wide as TMEM allows (the first version issued 480 N=64 MMAs per tile and
+//     was issue-bound): layer 1 = 12 MMAs of N=128, layer 2 = 24 of N=256, layer 3 = 4 chunks x
+//     60 of N=96 over two accumulator buffers (a chunk's epilogue overlaps the next chunk's
+//     MMAs): 276 MMAs per tile;
+//   * the MMA issue runs in the UNIFORM datapath: one asm statement per K stage (one elect.sync,
+//     addresses advanced inside the PTX, tc::mma_ts_stage), mbarrier waits as single asm loops and
+//     a shuffle-broadcast warp index let ptxas keep descriptors in uniform registers (UIADD3 +
+//     UTCHMMA, ~5 instructions per MMA). One asm statement per MMA cost 4 R2UR + ELECT + votes
+//     (~50 issue cycles, as long as an N=96 MMA executes); issuing from a divergent
+//     `if (lane == 0)` is worse still (nvcc wraps every UTCHMMA in an ELECT/BRA loop);
+//   * layers overlap inside a tile through fine-grained barriers: each layer-2 K slab waits only
+//     for its 32 act1 channels, layer-3 chunk 0 starts when layer 2's MMAs complete and each of
+//     its K stages waits only for its act2 quarter; the next tile's layer 0 is computed while the
+//     last chunk's MMAs run (b_a0free), and that chunk is read out and PARKED in registers so the
+//     next tile starts at once (its pooling happens inside the next tile's layer-2 MMA window);
+//   * code size is a first-order constraint: stage loops are not unrolled and the big blocks
+//     have one call site each (2.3 k SASS instructions; the first version's 9 k hot instructions
+//     cost 22 % of its non-idle stall samples in instruction fetch);
 //   * warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11
 //     epilogue (two warpgroups splitting the columns; warp%4 selects the TMEM lane quarter);
 //   * TMEM map (512 columns): [0,64) act0 | [64,320) D2/act2 | [320,448) D1/act1, and after
@@ -88,10 +99,12 @@ __device__ __forceinline__ uint64_t bdesc(uint32_t saddr, uint32_t sbo) {
 // POOL variant (the classifier / auto-encoder path): the input rows are the stacked copies SORTED
 // BY NODE (csrc/som_sort.cu) and the layer-3 epilogue, instead of storing the 384 channels of
 // every copy (1.47 GB at B=64,N=5000) for a separate index_max launch to re-read, reduces them
-// per node right away: lanes of a warp that share a node do one `redux.sync.max` on an
-// order-preserving integer key and the group leader one `red.global.max` into pool[b,c,node]
-// (models/index_max_ext semantics are restored by pool_finalize_kernel). first_pn_out is never
-// written.
+// per node right away: for every run of lanes that share a node (one run in 87 % of the warps)
+// a shuffle transpose-reduce over the RAW accumulators leaves one channel's maximum per lane
+// pair, which then applies scale/shift, converts to an order-preserving integer key and issues
+// ONE 16-lane `red.global.max` into keys[b,c,node]. models/index_max_ext semantics (max must be
+// > -1000, else the feature of copy 0) are restored when the keys are read
+// (knn_assemble_pool_kernel / pool_finalize_kernel). first_pn_out is never written.
 struct PoolArgs {
   const int32_t* node_sorted;  // [B,P] node id of each sorted row
   const int32_t* pos0;         // [B] sorted row of stacked copy 0

@@ -4,8 +4,9 @@
 // copies in their original order (models/networks.py:181-185). When `first_pn_out` itself is not
 // needed (classifier, auto-encoder) sonet_b200 never writes it: the tcgen05 kernel consumes the
 // stacked copies GROUPED BY NODE, so that the 32 lanes of an epilogue warp (32 consecutive
-// sorted copies) belong to one or two nodes and the per-node max of a channel is one warp `redux`
-// plus one atomic max (csrc/pointmlp_tc.cu, POOL variant). This file provides
+// sorted copies) belong to one or two nodes and the per-node max of 16 channels is one shuffle
+// transpose-reduce plus one 16-lane atomic max (csrc/pointmlp_tc.cu, POOL variant). This file
+// provides
 //
 //   som_sort_decenter_kernel   per cloud: bucket the k*N stacked copies by node (offsets from the
 //                              node counts, slots handed out by shared-memory atomics — the order
