@@ -403,18 +403,25 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
         }
         if (valid) {
           float* o = out + (static_cast<size_t>(b) * d.Cout + cg) * d.P + p;
-          auto emit = [&](uint32_t raw, int i) {
-            const int co = cg + i;
-            if (all_real || co < d.Cout) {
-              float y = fmaf(__uint_as_float(raw), d.inv, sh[i]);
-              if (arow) y += __ldg(arow + static_cast<size_t>(co) * d.G);
-              o[static_cast<size_t>(i) * d.P] = fmaxf(y, floor_v);
+          // 16 columns at a time: the gathered addends (one per output element, segmenter layer 1)
+          // are all loaded before the first dependent add, like the shift values above
+          auto emit16 = [&](const uint32_t (&v)[16], int i0) {
+            float ad[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              ad[i] = (arow != nullptr && (all_real || cg + i0 + i < d.Cout))
+                          ? __ldg(arow + static_cast<size_t>(cg + i0 + i) * d.G)
+                          : 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (all_real || cg + i0 + i < d.Cout) {
+                const float y = fmaf(__uint_as_float(v[i]), d.inv, sh[i0 + i]) + ad[i];
+                o[static_cast<size_t>(i0 + i) * d.P] = fmaxf(y, floor_v);
+              }
             }
           };
-#pragma unroll
-          for (int i = 0; i < 16; ++i) emit(v0[i], i);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) emit(v1[i], 16 + i);
+          emit16(v0, 0);
+          emit16(v1, 16);
         }
       }
       if (warp == 4 && it < 4) PW_TL(3, 2 * it + 1);
