@@ -85,3 +85,57 @@ def test_plugin_cpu_entry_points_known_answer(oracle_mod):
     assert torch.equal(index_max.forward_multi_thread_cpu(data, index, 13, 4), want)
     with pytest.raises(RuntimeError):
         index_max.forward_cpu(data, index.clamp(min=0) + 100, 13)
+
+
+def test_every_wrapper_call_names_a_bound_symbol_with_the_right_arity():
+    """Static check (no GPU): each `_call("sonet_...", args...)` / `_C.lib().sonet_...(args...)` in the
+    Python layer names a symbol of the ctypes table and passes as many arguments as it declares —
+    a typo here would otherwise only surface on a GPU box."""
+    import ast
+    import glob
+    import os
+
+    from sonet_b200 import _C
+    pkg = os.path.dirname(_C.__file__)
+    seen = set()
+    for path in sorted(glob.glob(os.path.join(pkg, "*.py"))):
+        tree = ast.parse(open(path).read(), path)
+        for node in ast.walk(tree):
+            if not isinstance(node, ast.Call):
+                continue
+            name, nargs = None, None
+            f = node.func
+            if isinstance(f, ast.Name) and f.id == "_call" and node.args and \
+                    isinstance(node.args[0], ast.Constant) and isinstance(node.args[0].value, str):
+                name, nargs = node.args[0].value, len(node.args) - 1
+            elif isinstance(f, ast.Attribute) and f.attr.startswith("sonet_"):
+                name, nargs = f.attr, len(node.args)
+            if name is None:
+                continue
+            where = "%s:%d" % (os.path.basename(path), node.lineno)
+            assert name in _C._SIGNATURES, "%s calls unknown symbol %s" % (where, name)
+            if not any(isinstance(x, ast.Starred) for x in node.args):
+                assert nargs == len(_C._SIGNATURES[name]), \
+                    "%s passes %d args to %s (declared %d)" % (where, nargs, name,
+                                                               len(_C._SIGNATURES[name]))
+            seen.add(name)
+    assert len(seen) >= 25, sorted(seen)
+
+
+def test_ctypes_arity_matches_the_header_prototypes():
+    """The ctypes argtypes of every symbol have as many entries as its prototype in
+    include/sonet_b200.h has parameters (a mismatch corrupts the call frame silently)."""
+    import os
+    import re
+
+    from sonet_b200 import _C
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "sonet_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)          # strip comments
+    protos = dict(re.findall(r"\b(sonet_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S))
+    assert set(protos) == set(_C._SIGNATURES)
+    for name, params in protos.items():
+        params = " ".join(params.split())
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_C._SIGNATURES[name]), "%s: header %d parameters, ctypes %d" % (
+            name, n, len(_C._SIGNATURES[name]))
