@@ -125,6 +125,7 @@ def test_every_wrapper_call_names_a_bound_symbol_with_the_right_arity():
 def test_ctypes_arity_matches_the_header_prototypes():
     """The ctypes argtypes of every symbol have as many entries as its prototype in
     include/sonet_b200.h has parameters (a mismatch corrupts the call frame silently)."""
+    import ctypes
     import os
     import re
 
@@ -136,6 +137,18 @@ def test_ctypes_arity_matches_the_header_prototypes():
     assert set(protos) == set(_C._SIGNATURES)
     for name, params in protos.items():
         params = " ".join(params.split())
-        n = 0 if params in ("", "void") else params.count(",") + 1
-        assert n == len(_C._SIGNATURES[name]), "%s: header %d parameters, ctypes %d" % (
-            name, n, len(_C._SIGNATURES[name]))
+        plist = [] if params in ("", "void") else [q.strip() for q in params.split(",")]
+        sig = _C._SIGNATURES[name]
+        assert len(plist) == len(sig), "%s: header %d parameters, ctypes %d" % (name, len(plist),
+                                                                              len(sig))
+        for q, ct in zip(plist, sig):           # and the same machine type, parameter by parameter
+            if "*" in q or "sonet_stream_t" in q:
+                want = ctypes.c_void_p
+            elif "long long" in q:
+                want = ctypes.c_longlong
+            elif re.match(r"(const\s+)?float\b", q):
+                want = ctypes.c_float
+            else:
+                assert re.match(r"(const\s+)?int\b", q), "%s: unhandled parameter type %r" % (name, q)
+                want = ctypes.c_int
+            assert ct is want, "%s: parameter %r is bound as %s" % (name, q, ct.__name__)
