@@ -17,9 +17,11 @@ per step inside the timed region. Rank 0 prints ONE JSON line.
             logits of step i
   roofline  dominant kernel (by measured device time) vs MEASURED_PEAKS.json, measured live with
             CUDA events around every C-ABI call of instrumented steps; `kernels` lists all of them
-  cpu_baseline   the oracle port of the reference's PyTorch-CPU path (oracle/oracle.py; the pool
-            runs in the reference's own compiled plugin when oracle/_ref exists) timed on this
-            box's host cores on a bounded sample
+  cpu_baseline   the reference's own PyTorch-CPU path — its unmodified classifier.Model from the
+            bytecode build product oracle/_ref/pyref, pool in its own compiled plugin ("kind":
+            "reference"; the oracle port only if that cannot be imported) — timed on this box's
+            host cores on a bounded sample (8 clouds of this run's inputs). Its logits are also
+            the parity check of the timed GPU steps ("parity")
   --impl reference   only that CPU arm, same JSON shape with "impl": "reference"
 """
 import argparse
@@ -118,22 +120,44 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-# ---- CPU arm: the oracle port of the reference path ----------------------------------------------------
-def cpu_arm(steps, warmup, sample_B=8):
-    """Time the oracle port (reference PyTorch-CPU dataflow) on the host cores."""
-    from oracle import build as obuild
-    obuild.build_c()
-    from oracle import oracle
-    from sonet_b200 import networks, synth
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    opt = synth.make_opt("classifier", batch_size=sample_B, input_pc_num=NPTS)
-    st_e = synth.synth_state_dict(networks.Encoder(opt), seed=1)
-    st_c = synth.synth_state_dict(networks.Classifier(opt), seed=2)
-    inp = synth.synth_inputs(sample_B, NPTS, seed=0)
-    kind = "port+reference-plugin" if oracle.ref_plugin() is not None else "port"
+# ---- CPU arm: the reference's own PyTorch-CPU path ---------------------------------------------------
+def _cpu_step_fn(sample_B, inp, st_e, st_c):
+    """Returns (step() -> score [sample_B, classes], set_threads(n), kind, pool_desc).
 
-    threads = {"n": cores}
+    kind "reference": the UNMODIFIED reference — its own models/classifier.py Model (set_input +
+    test_model, exactly the calls of modelnet/train.py:72-76) on its own networks/layers/som
+    modules, imported from the bytecode build product oracle/_ref/pyref (or /root/reference where
+    that exists) with the three shims of oracle/ref_shims.py; the pool runs in the reference's own
+    compiled plugin (forward_multi_thread_cpu, its faster CPU variant).
+    kind "port": the oracle restatement (oracle/oracle.py), only when the reference cannot be
+    imported on this machine."""
+    from sonet_b200 import synth
+    opt = synth.make_opt("classifier", batch_size=sample_B, input_pc_num=NPTS)
+    try:
+        from oracle import ref_shims
+        ref = ref_shims.install(prefer_pyref=True, pool_threads=os.cpu_count() or 1)
+        model = ref.classifier.Model(opt)
+        model.encoder.load_state_dict(st_e)
+        model.classifier.load_state_dict(st_c)
+        binary = bool(getattr(ref.index_max, "is_reference_binary", False))
+
+        def step():
+            model.set_input(inp["pc"], inp["sn"], inp["label"], inp["node"], inp["node_knn_I"])
+            model.test_model()
+            return model.score.detach()
+
+        def set_threads(n):
+            torch.set_num_threads(n)
+            ref.index_max.pool_threads = n
+        where = "oracle/_ref/pyref bytecode" if ref.root != ref_shims.REF else "/root/reference"
+        return step, set_threads, "reference", (
+            "reference classifier.Model.set_input/test_model from %s; index_max via %s"
+            % (where, "the reference's compiled forward_multi_thread_cpu" if binary
+               else "the C restatement (reference plugin not built)"))
+    except Exception as e:                                   # noqa: BLE001
+        why = "%s: %s" % (type(e).__name__, e)
+    from oracle import oracle
+    threads = {"n": os.cpu_count() or 1}
 
     def step():
         with torch.no_grad():
@@ -141,37 +165,52 @@ def cpu_arm(steps, warmup, sample_B=8):
                                        inp["node_knn_I"], fast_pool=threads["n"])
             return oracle.classifier_forward(st_c, o["feature"])
 
+    def set_threads(n):
+        torch.set_num_threads(n)
+        threads["n"] = n
+    return step, set_threads, "port", "oracle port (reference not importable here: %s)" % why
+
+
+def cpu_arm(steps, warmup, sample_B=8, inp=None):
+    """Time the reference's CPU path on the host cores, on a bounded sample (B=sample_B clouds of
+    the N=5000 workload). Returns the cpu_baseline dict and the scores of the sample."""
+    from oracle import build as obuild
+    obuild.build_c()
+    from sonet_b200 import networks, synth
+    cores = os.cpu_count() or 1
+    opt = synth.make_opt("classifier", batch_size=sample_B, input_pc_num=NPTS)
+    st_e = synth.synth_state_dict(networks.Encoder(opt), seed=1)
+    st_c = synth.synth_state_dict(networks.Classifier(opt), seed=2)
+    if inp is None:
+        inp = synth.synth_inputs(sample_B, NPTS, seed=0)
+    step, set_threads, kind, desc = _cpu_step_fn(sample_B, inp, st_e, st_c)
+
     # the reference path does not scale to every core count: probe a few thread counts and time
     # the best one (the faster reference number is the one compared against, SURVEY.md §8d)
     probe = {}
     for n in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16), min(cores, 8)},
                     reverse=True):
-        torch.set_num_threads(n)
-        threads["n"] = n
+        set_threads(n)
         step()
         t0 = time.perf_counter()
         step()
         probe[n] = time.perf_counter() - t0
     best = min(probe, key=probe.get)
-    torch.set_num_threads(best)
-    threads["n"] = best
+    set_threads(best)
     for _ in range(max(warmup - 1, 0)):
         step()
     times = []
+    score = None
     for _ in range(steps):
         t0 = time.perf_counter()
-        step()
+        score = step()
         times.append(time.perf_counter() - t0)
     per = sum(times) / len(times)
     return dict(value=sample_B / per, unit=UNIT, cores=best, host_cores=cores,
-                kind="port", pool=kind, ms_per_step=per * 1e3,
+                kind=kind, ms_per_step=per * 1e3,
                 thread_probe_s={str(k): round(v, 3) for k, v in probe.items()},
-                sample="%d steps of a B=%d x N=%d classifier forward (oracle port of the "
-                       "reference PyTorch-CPU path; index_max via %s), best of the probed "
-                       "thread counts, after warm-up"
-                       % (steps, sample_B, NPTS,
-                          "the reference's compiled forward_multi_thread_cpu" if "plugin" in kind
-                          else "the C restatement"))
+                sample="%d steps of a B=%d x N=%d classifier forward (%s), best of the probed "
+                       "thread counts, after warm-up" % (steps, sample_B, NPTS, desc)), score
 
 
 def run_reference_arm(args, rank):
@@ -179,7 +218,7 @@ def run_reference_arm(args, rank):
         return
     steps = max(1, min(args.steps, 5))
     warm = max(1, min(args.warmup, 2))
-    cb = cpu_arm(steps, warm)
+    cb, _ = cpu_arm(steps, warm)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -208,7 +247,9 @@ def kernel_report(profile_steps, peaks):
                 order.append(key)
             rows[key]["ms"].append(ms)
     out = []
-    hbm, tf = peaks["hbm_gbs"], peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    # per-kernel rows: each kernel is timed alone between CUDA events in a short eager pass at full
+    # boost clocks -> the BURST bf16 peak is the denominator (MEASURED_PEAKS.json "bf16_tflops")
+    hbm, tf = peaks["hbm_gbs"], peaks["bf16_tflops"]
     for key in order:
         r = rows[key]
         ms = sum(r["ms"]) / len(r["ms"])
@@ -341,6 +382,7 @@ def main():
         evs.append((e0, e1))
     barrier()
     wall = time.perf_counter() - wall0
+    timed_score = model.score.detach().clone()             # logits of the last timed step
     launches = ops.KERNEL_LAUNCHES - l0
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
@@ -408,7 +450,8 @@ def main():
     roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"],
                 "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"],
                 "traffic": NCU_TRAFFIC.get(dom["kernel"].split("#")[0]),
-                "peak_source": peaks["_source"] + (" bf16 sustained" if dom["bound"] == "tensor"
+                "peak_source": peaks["_source"] + (" bf16 burst (kernel timed alone)"
+                                                   if dom["bound"] == "tensor"
                                                    else " copy bandwidth"),
                 "ms": dom["ms"], "share_of_step": round(dom["ms"] / kernel_ms, 4),
                 "note": dom.get("note")}
@@ -465,9 +508,21 @@ def main():
                            "frac": round(byts / (ms_q * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
                            "traffic": None})
 
-    cpu_baseline = None
+    # CPU leg (rank 0, N=1): the reference's own CPU path on the first 8 clouds of THIS run's
+    # inputs with THIS run's weights — timed as the cpu_baseline, and its logits double as the
+    # parity check of the logits the timed GPU steps produced (outside every timed region)
+    cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_arm(steps=3, warmup=1)
+        sample = {k: inp[k][:8].contiguous() for k in keys}
+        cpu_baseline, ref_score = cpu_arm(steps=3, warmup=1, sample_B=8, inp=sample)
+        got = timed_score[:8].cpu()
+        err = float(((got - ref_score).abs() / ref_score.abs().clamp(min=1.0)).max())
+        parity = {"parity_checked": True, "against": cpu_baseline["kind"],
+                  "what": "logits of the timed steps (graph replay) for clouds 0-7 vs the CPU arm's "
+                          "logits on the same inputs/weights",
+                  "max_rel_err": err, "tol": 1e-4, "ok": err <= 1e-4}
+        if not parity["ok"]:
+            raise SystemExit("bench.py: GPU logits differ from the CPU reference: %.3e" % err)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
@@ -485,9 +540,11 @@ def main():
                 "gpu_launches": launches, "wall_s_timed_region": round(wall, 4),
                 "step_ms": {"min": round(min(step_ms), 4), "median": round(statistics.median(step_ms), 4),
                             "max": round(max(step_ms), 4)},
-                "clocks": clocks, "roofline": roofline, "kernels": kernels,
-                "standalone_kernels": standalone,
+                "clocks": clocks,
+                "roofline": dict(roofline, secondary=standalone), "kernels": kernels,
                 "cpu_baseline": cpu_baseline,
+                "parity": parity,
+                "parity_checked": bool(parity and parity["ok"]),
                 "checksum": float(out.double().sum().item())}
         print(json.dumps(line))
     if world > 1:

@@ -5,6 +5,16 @@
                                  lie under /root/reference/models/index_max_ext (read-only, never
                                  copied), with torch.utils.cpp_extension — only when /root/reference
                                  exists (this container). The GPU box uses the prebuilt file.
+  oracle/_ref/pyref/{models,util}/*.pyc   the REFERENCE's own Python modules compiled to CPython
+                                 bytecode (py_compile) from the sources where they lie — binary
+                                 build products like the .so above, never the sources. Python imports
+                                 sourceless .pyc files, so the unmodified reference Model classes
+                                 (models/{classifier,segmenter,autoencoder}.py) can run on the GPU
+                                 box, where /root/reference does not exist: (a) as the CPU arm of
+                                 bench.py ("kind": "reference") and (b) on top of sonet_b200's
+                                 networks in the drop-in GPU test. Same interpreter image on both
+                                 sides, so the bytecode magic matches; if it ever does not, the
+                                 importers fall back to the oracle port and say so.
 """
 import glob
 import os
@@ -65,7 +75,49 @@ def build_ref(force=False):
     return ref_plugin_path()
 
 
+PYREF = os.path.join(REFDIR, "pyref")
+REF_ROOT = "/root/reference"
+_PYREF_PKGS = ("models", "util")
+
+
+def pyref_root():
+    """Directory holding the bytecode-compiled reference packages, or None if not built / stale
+    for this interpreter."""
+    import importlib.util
+    probe = os.path.join(PYREF, "models", "classifier.pyc")
+    if not os.path.exists(probe):
+        return None
+    with open(probe, "rb") as f:
+        if f.read(4) != importlib.util.MAGIC_NUMBER:
+            return None
+    return PYREF
+
+
+def build_pyref(force=False):
+    """py_compile every top-level module of the reference's `models` and `util` packages into
+    oracle/_ref/pyref (sourceless .pyc). Only possible where /root/reference exists."""
+    import py_compile
+    if not os.path.isdir(os.path.join(REF_ROOT, "models")):
+        return pyref_root()
+    if pyref_root() and not force:
+        return PYREF
+    n = 0
+    for pkg in _PYREF_PKGS:
+        src_dir = os.path.join(REF_ROOT, pkg)
+        dst_dir = os.path.join(PYREF, pkg)
+        os.makedirs(dst_dir, exist_ok=True)
+        for f in sorted(os.listdir(src_dir)):
+            if not f.endswith(".py"):
+                continue
+            py_compile.compile(os.path.join(src_dir, f), cfile=os.path.join(dst_dir, f + "c"),
+                               dfile="%s/%s" % (pkg, f), doraise=True)
+            n += 1
+    print("[oracle] compiled %d reference modules to bytecode -> %s" % (n, os.path.relpath(PYREF, HERE)))
+    return PYREF
+
+
 if __name__ == "__main__":
     build_c(force="--force" in sys.argv)
     if "--no-ref" not in sys.argv:
         build_ref(force="--force-ref" in sys.argv)
+        build_pyref(force="--force-ref" in sys.argv)

@@ -1,7 +1,9 @@
-"""ref_shims.py — TEST INFRASTRUCTURE. Import the UNMODIFIED reference (/root/reference) on CPU.
+"""ref_shims.py — TEST INFRASTRUCTURE. Import the UNMODIFIED reference on CPU.
 
-Only usable in the build container (the GPU box has no /root/reference). Three shims, as
-established in SURVEY.md §0 / Appendix B:
+Source of the reference modules: /root/reference when it exists (the build container), else the
+bytecode build product oracle/_ref/pyref (sourceless .pyc compiled from those sources by
+oracle/build.py:build_pyref — what travels to the GPU box). Three shims, as established in
+SURVEY.md §0 / Appendix B:
   1. empty stub modules for matplotlib / mpl_toolkits (imported but unused, models/networks.py:14-15);
   2. a `faiss` stub whose IndexFlatL2 is an exact brute-force search (only ChamferLoss uses it);
   3. module `index_max` = the reference's own plugin compiled in place (oracle/_ref), with
@@ -17,8 +19,17 @@ import torch
 REF = "/root/reference"
 
 
+def ref_root(prefer_pyref=False):
+    """Where the reference's `models` / `util` packages are importable from, or None."""
+    from . import build as _b
+    have_src = os.path.isdir(os.path.join(REF, "models"))
+    if have_src and not prefer_pyref:
+        return REF
+    return _b.pyref_root() or (REF if have_src else None)
+
+
 def available():
-    return os.path.isdir(os.path.join(REF, "models"))
+    return ref_root() is not None
 
 
 class _IndexFlatL2:
@@ -37,11 +48,15 @@ class _IndexFlatL2:
         return D.numpy(), I.numpy()
 
 
-def install(use_ref_plugin=True):
-    """Register the shims and put the reference on sys.path. Returns the reference's modules."""
-    if not available():
-        raise RuntimeError("/root/reference is not present on this machine")
-    for name in ("matplotlib", "matplotlib.pyplot", "mpl_toolkits", "mpl_toolkits.mplot3d"):
+def install(use_ref_plugin=True, prefer_pyref=False, pool_threads=None):
+    """Register the shims and put the reference on sys.path. Returns the reference's modules.
+    pool_threads: when set, CPU tensors handed to index_max.forward_cuda go to the reference's
+    forward_multi_thread_cpu with that many threads (its faster CPU variant, index_max.cpp:33-70)
+    instead of forward_cpu — used by the timed CPU arm only."""
+    root = ref_root(prefer_pyref)
+    if root is None:
+        raise RuntimeError("neither /root/reference nor oracle/_ref/pyref is present on this machine")
+    for name in ("matplotlib", "matplotlib.pyplot", "mpl_toolkits", "mpl_toolkits.mplot3d", "h5py"):
         sys.modules.setdefault(name, types.ModuleType(name))
     sys.modules["mpl_toolkits.mplot3d"].Axes3D = object
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
@@ -67,8 +82,15 @@ def install(use_ref_plugin=True):
     if plugin is not None:
         shim.forward_cpu = plugin.forward_cpu
         shim.forward_multi_thread_cpu = plugin.forward_multi_thread_cpu
-        shim.forward_cuda = lambda data, index, K: plugin.forward_cpu(data, index, K)
-        shim.forward_cuda_shared_mem = shim.forward_cuda
+        shim.pool_threads = pool_threads      # mutable: the timed CPU arm probes thread counts
+
+        def _fwd(data, index, K):
+            if shim.pool_threads:
+                return plugin.forward_multi_thread_cpu(
+                    data, index, K, max(1, min(int(shim.pool_threads), data.shape[1])))
+            return plugin.forward_cpu(data, index, K)
+        shim.forward_cuda = _fwd
+        shim.forward_cuda_shared_mem = _fwd
         shim.is_reference_binary = True
     else:
         shim.forward_cpu = oracle.index_max
@@ -77,8 +99,8 @@ def install(use_ref_plugin=True):
         shim.is_reference_binary = False
     sys.modules["index_max"] = shim
 
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import models.autoencoder as ref_autoencoder
     import models.classifier as ref_classifier
     import models.losses as ref_losses
@@ -87,4 +109,4 @@ def install(use_ref_plugin=True):
     import util.som as ref_som
     return types.SimpleNamespace(classifier=ref_classifier, segmenter=ref_segmenter,
                                  autoencoder=ref_autoencoder, networks=ref_networks,
-                                 losses=ref_losses, som=ref_som, index_max=shim)
+                                 losses=ref_losses, som=ref_som, index_max=shim, root=root)

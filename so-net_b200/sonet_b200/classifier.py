@@ -43,6 +43,7 @@ class Model():
         self.test_accuracy = torch.zeros(1, dtype=torch.float32)
         self._use_graph = False
         self._graphs = {}
+        self._graph_stream = None
 
     # ---- CUDA-graph replay of the eval forward ---------------------------------------------------
     def enable_cuda_graph(self, flag=True):
@@ -53,6 +54,16 @@ class Model():
         next replay of the same buffer set overwrites; graphs are re-captured when an input shape or
         any parameter/buffer version changes."""
         self._use_graph = bool(flag) and self._dev.type == "cuda"
+        self._graphs = {}
+        if self._use_graph and self._graph_stream is None:
+            self._graph_stream = torch.cuda.Stream(device=self._dev)
+
+    def invalidate(self):
+        """Forget folded/packed weights and captured graphs (call after editing parameters
+        through `.data`, which does not bump tensor versions — see layers.invalidate)."""
+        from . import layers
+        layers.invalidate(self.encoder)
+        layers.invalidate(self.classifier)
         self._graphs = {}
 
     def _state_key(self, s):
@@ -71,29 +82,47 @@ class Model():
         self.score = self.classifier(self.feature, None)
         self.loss = self.softmax_criteria(self.score, self.label)
 
+    # encoder attributes that other code reads after a forward (models/segmenter.py:90-108 style)
+    _ENC_PUBLIC = ("som_node", "first_pn_out_masked_max", "knn_center_1", "knn_feature_1",
+                   "final_pn_out", "feature", "_assign", "_lazy_src")
+    _ENC_LAZY = ("_mask", "_centers", "_x_aug", "_first_pn_out")
+
     def _test_model_graph(self):
         s = self._sets[self._cur]
         cur = torch.cuda.current_stream(self._dev)
         cur.wait_event(s.ready)
         key = self._state_key(s)
         g = self._graphs.get(self._cur)
+        enc = self.encoder
         with torch.no_grad():
             if g is None or g["key"] != key:
-                for _ in range(2):               # warm every host-side cache (folded/packed weights)
-                    self._eval_forward()
+                # warm-up AND capture run on the model's capture stream, so per-stream scratch
+                # (the pool keys) is created and left clean before the capture starts
+                gs = self._graph_stream
+                gs.wait_stream(cur)
+                with torch.cuda.stream(gs):
+                    for _ in range(2):           # warm every host-side cache (folded/packed weights)
+                        self._eval_forward()
                 torch.cuda.synchronize(self._dev)
                 graph = torch.cuda.CUDAGraph()
                 k0, c0 = ops.KERNEL_LAUNCHES, ops.LAUNCHES
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, stream=gs):
                     self._eval_forward()
                 g = dict(key=key, graph=graph, kernels=ops.KERNEL_LAUNCHES - k0,
                          calls=ops.LAUNCHES - c0, feature=self.feature, score=self.score,
-                         loss=self.loss)
+                         loss=self.loss,
+                         enc={n: getattr(enc, n) for n in self._ENC_PUBLIC if hasattr(enc, n)})
                 self._graphs[self._cur] = g
             g["graph"].replay()
         ops.KERNEL_LAUNCHES += g["kernels"]      # the replay launches the captured kernels
         ops.LAUNCHES += g["calls"]
         self.feature, self.score, self.loss = g["feature"], g["score"], g["loss"]
+        # the encoder's cached attributes point at THIS graph's static buffers again (two input
+        # sets = two graphs = two buffer sets); lazily derived ones are recomputed on demand
+        for n, v in g["enc"].items():
+            setattr(enc, n, v)
+        for n in self._ENC_LAZY:
+            setattr(enc, n, None)
         s.consumed.record(cur)
 
     def _bind(self, s):

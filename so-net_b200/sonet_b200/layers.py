@@ -1,11 +1,16 @@
 """Layer classes with the reference's constructor signatures and state_dict keys
 (models/layers.py:22-432), running on the sm_100a kernels of libsonet_b200 in eval/no-grad mode.
 
-Dispatch rule (SURVEY.md §8b "Autograd"): the hand-written forward kernels are used whenever the
-module is in eval() mode and autograd is not recording (the metric: eval forward, torch.no_grad()).
-In train() mode, or when gradients are required, the layers compose differentiable PyTorch ops on
-the GPU exactly as the reference does — that is the reference's own training path, not a CPU
-fallback. Non-default options ('instance' norm, elu/swish/leakyrelu) always take the PyTorch path.
+Dispatch rule (SURVEY.md §8b "Autograd"): the hand-written forward kernels run whenever the module
+is in eval() mode and no INPUT tensor carries a gradient — with or without torch.no_grad(), because
+the reference's own test loop (models/classifier.py:101-105, modelnet/train.py:72-76) calls
+test_model() in eval mode WITHOUT no_grad and must still land on the hot path. An eval-mode forward
+therefore returns tensors without grad_fn: calling backward() on them fails loudly ("does not
+require grad") instead of silently dropping parameter gradients. In train() mode, when an input
+requires grad (saliency / adversarial use in eval mode), or when EVAL_AUTOGRAD is set, the layers
+compose differentiable PyTorch ops on the GPU exactly as the reference does — the reference's own
+training path, not a CPU fallback. Non-default options ('instance' norm, elu/swish/leakyrelu)
+always take the PyTorch path.
 """
 import math
 import os
@@ -18,8 +23,16 @@ from torch.nn.modules.batchnorm import _BatchNorm
 from . import operations, ops
 
 
+# Set to True to make eval-mode forwards differentiable w.r.t. the parameters as well (the
+# PyTorch composition); the default keeps eval() = inference kernels.
+EVAL_AUTOGRAD = False
+
+
 def _fast_ok(module, *tensors):
-    if module.training or torch.is_grad_enabled():
+    if module.training:
+        return False
+    if torch.is_grad_enabled() and (EVAL_AUTOGRAD or any(t is not None and t.requires_grad
+                                                         for t in tensors)):
         return False
     return all(t is not None and t.is_cuda and t.dtype == torch.float32 for t in tensors)
 
@@ -112,6 +125,22 @@ class _FoldedParams:
         if self.wt is None:
             self.wt = self.w.t().contiguous()
         return self.wt, self.shift
+
+
+def invalidate(module):
+    """Drop every derived weight cache (BN-folded weights, tcgen05 packings) below `module`.
+
+    The caches are keyed on (data_ptr, tensor._version) of the parameters and BN statistics, which
+    optimizer steps, load_state_dict() and in-place tensor ops all bump. Writes through `.data`
+    (`p.data.mul_(..)`, `w.data.copy_(..)` — an idiom of the reference code base,
+    e.g. models/networks.py:366) do NOT bump the version counter: call this after such edits."""
+    for m in module.modules():
+        f = getattr(m, "_folded", None)
+        if isinstance(f, _FoldedParams):
+            f._key = None
+        for attr in ("_tc_key", "_l1_key"):
+            if hasattr(m, attr):
+                setattr(m, attr, None)
 
 
 class MyLinear(nn.Module):
@@ -344,7 +373,8 @@ class KNNModule(nn.Module):
                 and all(l._fast_eligible() for l in self.layers)
                 and (precomputed_knn_I is None or precomputed_knn_I.is_cuda))
 
-    def forward_pooled(self, coordinate, pool, precomputed_knn_I, K, center_type, epoch=None):
+    def forward_pooled(self, coordinate, pool, precomputed_knn_I, K, center_type, epoch=None,
+                       owner=None):
         """forward() for the fused-pool path: `pool` = (keys [B,C,M] i32, p0 [B,C]) as left by
         ops.pointresnet_tc_pool(finalize=False). Returns (center, feature, masked_max [B,C,M]) or
         None when this module cannot take the fused route (the caller then finalizes the pool)."""
@@ -355,11 +385,13 @@ class KNNModule(nn.Module):
             return None
         coord = coordinate.detach().contiguous()
         if precomputed_knn_I is not None:
-            assert precomputed_knn_I.size()[2] >= K
+            if precomputed_knn_I.size()[2] < K:
+                return None      # the unfused forward() raises the reference's assertion
             knn_I = precomputed_knn_I.contiguous()
         else:
             knn_I = ops.node_knn(coord, K)
-        center, h, masked_max = ops.knn_assemble_pool(coord, keys, p0, knn_I, K, center_type)
+        center, h, masked_max = ops.knn_assemble_pool(coord, keys, p0, knn_I, K, center_type,
+                                                      owner=owner)
         for layer in self.layers:
             h = layer.forward_points(h)
         feature = ops.rowmax(h.view(B, h.shape[1], M, K))

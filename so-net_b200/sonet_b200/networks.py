@@ -19,7 +19,7 @@ import torch.nn as nn
 
 from . import ops, som
 from .layers import (EquivariantLayer, KNNModule, MyConv2d, MyLinear, PointNet, PointResNet,
-                     UpConv)
+                     UpConv, _fast_ok)
 
 
 def _bn_kwargs(opt):
@@ -92,6 +92,8 @@ class Encoder(nn.Module):
         # tcgen05 PointResNet and never write it. Callers that read encoder.first_pn_out every
         # forward (the segmenter) set this to False to avoid the lazy recomputation.
         self.fuse_pool = True
+        self._fpo_demand = False     # set once a caller has read first_pn_out lazily (see below)
+        self._pool_keys = ops.PoolKeys()
 
     # ---- lazily materialised public attributes (API of models/networks.py:127, 169) -----------
     @property
@@ -126,6 +128,10 @@ class Encoder(nn.Module):
         """[B,384,kN] output of the first PointResNet (models/networks.py:176). On the fused
         path it is only computed when somebody reads it."""
         if self._first_pn_out is None and self._lazy_src is not None:
+            # a caller that reads first_pn_out after a fused forward (the reference's unmodified
+            # models/segmenter.py:100-105 does, every forward) pays one recomputation; from the
+            # next forward on the encoder keeps the unfused path for it
+            self._fpo_demand = True
             with torch.no_grad():
                 self._first_pn_out = self.first_pointnet(self._materialise_x_aug(),
                                                          self._lazy_src[4])
@@ -144,7 +150,7 @@ class Encoder(nn.Module):
         k = opt.k
         M = node.size()[2]
         use_sn = opt.surface_normal == True  # noqa: E712
-        fast = not (self.training or torch.is_grad_enabled())
+        fast = _fast_ok(self, x, sn if use_sn else x)    # eval mode, no input gradient
 
         # SOM nodes come from the loader (models/networks.py:123-124)
         self.som_builder.node = node.detach().to(torch.float32).contiguous()
@@ -154,7 +160,8 @@ class Encoder(nn.Module):
         xd = x.detach().contiguous()
         snd = sn.detach().contiguous() if use_sn else None
         fpn = self.first_pointnet
-        fused = (fast and self.fuse_pool and M <= 256 and fpn.layers[0].fast(xd)
+        fused = (fast and self.fuse_pool and not self._fpo_demand and M <= 256
+                 and fpn.layers[0].fast(xd)
                  and fpn._tc_eligible(6 if use_sn else 3, None))
         group = fused and ops.som_group_fits(xd.shape[2], M, k, xd.device)
         a = ops.som_assign(xd, self.som_builder.node, k, want_stats=not group)
@@ -176,13 +183,14 @@ class Encoder(nn.Module):
             if not group:
                 xs, ns, p0 = ops.som_sort_decenter(xd, snd, self.som_node, idx32, a["count"], k)
             blob, fpar = fpn._tc_params()
-            pooled = ops.pointresnet_tc_pool(xs, blob, fpar, ns, p0, M, finalize=False)
+            pooled = ops.pointresnet_tc_pool(xs, blob, fpar, ns, p0, M, finalize=False,
+                                             owner=self._pool_keys)
             done = None
             if opt.som_k >= 2:   # pool_finalize folds into the KNN module's input assembly
                 done = self.knnlayer.forward_pooled(self.som_node, pooled, node_knn_I, opt.som_k,
-                                                    opt.som_k_type, epoch)
+                                                    opt.som_k_type, epoch, owner=self._pool_keys)
             if done is None:
-                self.first_pn_out_masked_max = ops.pool_finalize(*pooled)
+                self.first_pn_out_masked_max = ops.pool_finalize(*pooled, owner=self._pool_keys)
                 pooled = None
             else:
                 self.knn_center_1, self.knn_feature_1, self.first_pn_out_masked_max = done
@@ -348,7 +356,13 @@ class Segmenter(nn.Module):
         (1.3 GB at B=32,N=1024) is never written.
         """
         if not (self.layer1.fast(first_pn_out) and self.opt.som_k >= 2):
-            g = lambda t: ops.gather_points(t.contiguous(), min_idx_i32)  # noqa: E731
+            if self.layer1.fast(node_first, node_final):
+                g = lambda t: ops.gather_points(t.contiguous(), min_idx_i32)  # noqa: E731
+            else:
+                # training / grad mode: torch.gather as in models/segmenter.py:96-98, so that the
+                # encoder receives gradient through the three node-level feature maps
+                i64 = min_idx_i32.long().unsqueeze(1)
+                g = lambda t: torch.gather(t, 2, i64.expand(-1, t.shape[1], -1))  # noqa: E731
             return self.forward(x_decentered, x, centers, sn, label, first_pn_out, g(node_first),
                                 g(node_knn), g(node_final), feature)
         B, N = x.size()[0], x.size()[2]

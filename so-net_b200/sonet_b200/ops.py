@@ -379,20 +379,49 @@ def som_group_decenter(x, sn, min_idx_i32, M, k):
     return xs, ns, p0, count, cmean
 
 
-_POOL_KEYS = {}   # (device, B, M) -> persistent key buffer (self-resetting: finalize re-inits it)
+class PoolKeys:
+    """Per-owner (one per Encoder), per-(device, B, M, stream) key buffers of the fused per-node
+    max. The kernels keep the invariant "keys are all-minimum between forwards" themselves
+    (pool_finalize / knn_assemble_pool reset every key they read); `dirty` covers the failure
+    window between the pool launch and its finalisation: if anything raises in between, the next
+    acquire() re-initialises the buffer instead of silently maxing against a stale batch."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def acquire(self, dev, B, M, stream):
+        kk = (dev, int(B), int(M), int(stream))
+        ent = self._bufs.get(kk)
+        if ent is None:
+            ent = self._bufs[kk] = dict(
+                keys=torch.empty((B, 384, M), dtype=torch.int32, device=dev), dirty=True)
+        if ent["dirty"]:
+            _call("sonet_pool_keys_init", _C.ptr(ent["keys"]), ent["keys"].numel(), stream)
+        ent["dirty"] = True          # until release()
+        self._last = ent
+        return ent["keys"]
+
+    def release(self, keys):
+        for ent in self._bufs.values():
+            if ent["keys"] is keys:
+                ent["dirty"] = False
 
 
-def pool_finalize(keys, p0):
+_DEFAULT_POOL_KEYS = PoolKeys()   # for direct ops.pointresnet_tc_pool callers (tests, tools)
+
+
+def pool_finalize(keys, p0, owner=None):
     """Pool keys [B,C,M] i32 + copy-0 features [B,C] -> first_pn_out_masked_max [B,C,M]; resets
     the keys."""
     B, C, M = keys.shape
     with torch.cuda.device(keys.device):
         out = torch.empty((B, C, M), dtype=torch.float32, device=keys.device)
         _call("sonet_pool_finalize", _C.ptr(keys), _C.ptr(p0), B, C, M, _C.ptr(out), _stream(keys))
+    (owner or _DEFAULT_POOL_KEYS).release(keys)
     return out
 
 
-def knn_assemble_pool(coord, keys, p0, idx, K, center_type):
+def knn_assemble_pool(coord, keys, p0, idx, K, center_type, owner=None):
     """knn_assemble reading the per-node maxima from the pool keys (pool_finalize folded in).
     -> (center [B,3,M], x_aug [B,3+C,M*K], masked_max [B,C,M])."""
     _chk(coord, "coordinate", torch.float32)
@@ -409,10 +438,11 @@ def knn_assemble_pool(coord, keys, p0, idx, K, center_type):
         mm = torch.empty((B, C, M), dtype=torch.float32, device=dev)
         _call("sonet_knn_assemble_pool_f32", _C.ptr(coord), _C.ptr(keys), _C.ptr(p0), _C.ptr(idx), B,
               C, M, int(K), Kstride, ct, _C.ptr(mm), _C.ptr(center), _C.ptr(x_aug), _stream(keys))
+    (owner or _DEFAULT_POOL_KEYS).release(keys)
     return center, x_aug, mm
 
 
-def pointresnet_tc_pool(x_sorted, blob, fparams, node_sorted, pos0, M, finalize=True):
+def pointresnet_tc_pool(x_sorted, blob, fparams, node_sorted, pos0, M, finalize=True, owner=None):
     """Fused tcgen05 PointResNet + per-node max: -> first_pn_out_masked_max [B,384,M], or with
     finalize=False the raw (keys [B,384,M] i32, p0 [B,384]) for knn_assemble_pool / pool_finalize."""
     _chk(x_sorted, "x_sorted", torch.float32)
@@ -423,19 +453,14 @@ def pointresnet_tc_pool(x_sorted, blob, fparams, node_sorted, pos0, M, finalize=
     B, Cin, P = x_sorted.shape
     dev = x_sorted.device
     with torch.cuda.device(dev):
-        kk = (dev, B, int(M))
-        keys = _POOL_KEYS.get(kk)
-        if keys is None:
-            keys = torch.empty((B, 384, M), dtype=torch.int32, device=dev)
-            _call("sonet_pool_keys_init", _C.ptr(keys), keys.numel(), _stream(x_sorted))
-            _POOL_KEYS[kk] = keys
+        keys = (owner or _DEFAULT_POOL_KEYS).acquire(dev, B, M, _stream(x_sorted))
         p0 = torch.empty((B, 384), dtype=torch.float32, device=dev)
         _call("sonet_pointresnet_tc_pool_forward", _C.ptr(x_sorted), Cin, B, P, _C.ptr(blob),
               _C.ptr(fparams), _C.ptr(node_sorted), _C.ptr(pos0), int(M), _C.ptr(keys), _C.ptr(p0),
               _stream(x_sorted))
     if not finalize:
         return keys, p0
-    return pool_finalize(keys, p0)
+    return pool_finalize(keys, p0, owner)
 
 
 def som_query_topk(x, node, k):

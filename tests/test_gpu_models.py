@@ -159,6 +159,46 @@ def test_full_size_shard_invariance_and_determinism():
     assert torch.isfinite(full).all()
 
 
+def _assert_encoder_slice_vs_oracle(oracle_mod, enc, o, k, n_clouds):
+    """Every node-level tensor of the first n_clouds clouds against the oracle (1e-4), k-sets exact."""
+    assert torch.equal(oracle_mod.canon_sets(enc.min_idx[:n_clouds].cpu(), k),
+                       oracle_mod.canon_sets(o["min_idx"], k))
+    for n in ("som_node", "first_pn_out_masked_max", "knn_center_1", "knn_feature_1",
+              "final_pn_out", "feature"):
+        assert_close(getattr(enc, n)[:n_clouds], o[n], n)
+
+
+def test_cfg2_benchmarked_pipeline_vs_oracle(oracle_mod):
+    """The EXACT pipeline bench.py times — classifier.Model with enable_cuda_graph(True) at
+    BASELINE.json configs[1] (B=64, N=5000: som_group + fused tcgen05 PointResNet/pool at
+    kN=15000 + graph replay) — against the oracle on a 3-cloud slice: k-sets exact, som_node,
+    first_pn_out_masked_max, knn_feature_1, final_pn_out, feature and score within 1e-4
+    (|a-b| <= 1e-4 * max(|b|,1)). Checked on the capture run AND on a replay with new inputs."""
+    from sonet_b200 import synth
+    B, N, S = 64, 5000, 3
+    opt = synth.make_opt("classifier", batch_size=B, input_pc_num=N)
+    st = build_states("classifier", opt, seed=61)
+    m = _classifier(opt, st)
+    m.enable_cuda_graph(True)
+    keys = ("pc", "sn", "label", "node", "node_knn_I")
+    cpu_opt = synth.make_opt("classifier", batch_size=S, input_pc_num=N)
+    # seeds 61/62 -> buffer set 1, then 0 (capture runs); 63/64 -> replays of both graphs.
+    # 'uniform' nodes on the last one: empty nodes through the fused pool at full size
+    for i, (seed, mode) in enumerate(((61, "sampled"), (62, "sampled"), (63, "sampled"),
+                                      (64, "uniform"))):
+        inp = synth.synth_inputs(B, N, seed=seed, node_mode=mode)
+        m.set_input(*[inp[k] for k in keys])
+        m.test_model()
+        if i in (1, 2):
+            continue                     # oracle time: check the first capture and both replays' ends
+        o = oracle_mod.encoder_forward(st["encoder"], cpu_opt, inp["pc"][:S], inp["sn"][:S],
+                                       inp["node"][:S], inp["node_knn_I"][:S])
+        _assert_encoder_slice_vs_oracle(oracle_mod, m.encoder, o, 3, S)
+        assert_close(m.score[:S], oracle_mod.classifier_forward(st["head"], o["feature"]), "score")
+        if mode == "uniform":
+            assert int((o["mask_row_max"] == 0).sum()) > 0, "case must contain empty nodes"
+
+
 def test_training_step_runs_on_gpu_and_changes_weights():
     """train() mode composes differentiable PyTorch ops around the kernels' indices."""
     from sonet_b200 import synth
@@ -234,6 +274,13 @@ def test_autoencoder_cfg4_full_size(oracle_mod):
     assert_close(m.chamfer_criteria.loss_array, arr[:16], "cfg-4 shard consistency", 1e-5)
     o = oracle_mod.chamfer(pred[:2].cpu(), inp["pc"][:2])
     assert_close(arr[:2], o["loss_array"], "cfg-4 chamfer loss_array slice vs oracle")
+    # the N=5000 encoder of this config against the oracle (2-cloud slice, 1e-4)
+    cpu_opt = synth.make_opt("autoencoder", batch_size=2, input_pc_num=N)
+    m.set_input(*[inp[k] for k in keys])
+    m.test_model()
+    oe = oracle_mod.encoder_forward(st["encoder"], cpu_opt, inp["pc"][:2], inp["sn"][:2],
+                                    inp["node"][:2], inp["node_knn_I"][:2])
+    _assert_encoder_slice_vs_oracle(oracle_mod, m.encoder, oe, 3, 2)
 
 
 def test_cuda_graph_replay_matches_eager_and_tracks_changes():
