@@ -136,7 +136,8 @@ def _cpu_step_fn(sample_B, inp, st_e, st_c):
     try:
         from oracle import ref_shims
         ref = ref_shims.install(prefer_pyref=True, pool_threads=os.cpu_count() or 1)
-        model = ref.classifier.Model(opt)
+        with ref_shims.cpu_only():       # the SOM node buffer follows cuda availability, not opt.device
+            model = ref.classifier.Model(opt)
         model.encoder.load_state_dict(st_e)
         model.classifier.load_state_dict(st_c)
         binary = bool(getattr(ref.index_max, "is_reference_binary", False))

@@ -97,6 +97,25 @@ int sonet_som_decenter(const float* x, const float* sn, const float* cluster_mea
                        const int32_t* min_idx_i32, int B, int N, int M, int k,
                        float* centers, float* x_aug, sonet_stream_t stream);
 
+/* ---- f-4: batch-SOM training --------------------------------------------------------------------
+ * Replaces BatchSOM.batch_update / BatchSOM.optimize (util/som.py:295-366): T iterations of
+ * {nearest-node assignment, per-node mean, neighbourhood-weighted node update} per cloud, in ONE
+ * launch (a persistent CTA per cloud keeps cloud, nodes and assignment in shared memory).
+ * x [B,3,N]; node_init [3,M] shared by every cloud (node_init_batched = 0; BatchSOM.node_init,
+ * som.py:209-212) or [B,3,M] (node_init_batched = 1; a single batch_update on the current nodes);
+ * weights [T,M,M] f32: weights[t][m][j] = get_weighting_matrix(sigma_t)[m] at grid cell j
+ * (som.py:232-235); lr [T] f32. node_out [B,3,M] (may alias a batched node_init).
+ * last_idx (nullable) [B,N] i32 = the assignment computed in the last iteration.
+ * Numerics: distances bit-equal to ((x-node)**2).sum(1), first minimal node on ties
+ * (torch.min); sums accumulated in fp64 in a fixed order and rounded once (the reference's
+ * cascade torch.sum is ~1 ulp accurate; plain fp32 accumulation diverges through assignment
+ * flips); mean = sum / (count + 1e-5f); node += sum_m ((mean_m - node_j) * occupied_m) * W[m][j] * lr.
+ * M <= 256; N up to ~17k points with the cloud resident in shared memory (larger N re-reads x
+ * through L2; N <= ~220k). */
+int sonet_som_train(const float* x, const float* node_init, int node_init_batched,
+                    const float* weights, const float* lr, int T, int B, int N, int M,
+                    float* node_out, int32_t* last_idx, sonet_stream_t stream);
+
 /* ---- a-4/a-5/a-8/a-9/a-10: point-wise shared MLP layer (1x1 conv + folded BN + ReLU) ---------
  * Replaces EquivariantLayer.forward / MyConv2d(1x1).forward in eval mode
  * (models/layers.py:203-210, 282-296): out[b,co,p] = act(scale[co]*sum_ci W[co,ci]*X[b,ci,p] +

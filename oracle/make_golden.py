@@ -194,6 +194,42 @@ def gen_autoencoder(ref, tag, B, N, seed):
     print("wrote", tag)
 
 
+def som_cloud(rs, B, N):
+    """Seeded surface-like clouds for SOM training: points on randomly scaled ellipsoids."""
+    x = rs.normal(size=(B, 3, N)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    x *= rs.uniform(0.3, 1.0, size=(B, 3, 1)).astype(np.float32)
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def gen_som_train(ref):
+    """§8f-4: BatchSOM.optimize / batch_update of the reference (util/som.py:295-366) on seeded
+    clouds; pins the oracle restatement bit-exactly against it."""
+    rs = np.random.RandomState(17)
+    B, N = 3, 700
+    x = torch.from_numpy(som_cloud(rs, B, N))
+    som = ref.som.BatchSOM(8, 8, 3, 0, B)
+    out = dict(x=x.numpy(), node_init_value=som.node_init_value.numpy().copy())
+    som.node_init(B)
+    som.batch_update(x, 0.5, 0.4)                       # one step from the potential-field start
+    out["node_after_1"] = som.node.numpy().copy()
+    som.batch_update(x, 0.31, 0.22)                     # a second one with a narrower neighbourhood
+    out["node_after_2"] = som.node.numpy().copy()
+    init_w = oracle.som_init_weighting_matrix(8, 8)
+    assert torch.equal(init_w, som.init_weighting_matrix)
+    n0 = som.node_init_value.unsqueeze(0).expand(B, -1, -1).contiguous()
+    n1, _ = oracle.som_batch_update(n0, x, init_w, 0.5, 0.4)
+    n2, _ = oracle.som_batch_update(n1, x, init_w, 0.31, 0.22)
+    assert torch.equal(n1, torch.from_numpy(out["node_after_1"])), "oracle batch_update != reference"
+    assert torch.equal(n2, torch.from_numpy(out["node_after_2"]))
+    som.optimize(x)
+    out["node_optimized"] = som.node.numpy().copy()
+    o = oracle.som_optimize(x, som.node_init_value, 8, 8)
+    assert torch.equal(o, som.node), "oracle som_optimize != reference"
+    np.savez_compressed(os.path.join(GOLDEN, "som_train.npz"), **out)
+    print("som_train.npz: reference BatchSOM == oracle restatement (bit-exact)")
+
+
 def gen_state_keys(ref):
     """Names and shapes of every state_dict tensor of the reference networks (checkpoint
     compatibility contract, SURVEY.md §5 'Checkpoint / resume')."""
@@ -221,7 +257,13 @@ def main():
     torch.set_num_threads(8)
     os.makedirs(GOLDEN, exist_ok=True)
     ref = ref_shims.install()
+    only = sys.argv[1:]
+    if only:                                     # e.g. `python -m oracle.make_golden som_train`
+        for name in only:
+            globals()["gen_" + name](ref)
+        return
     gen_index_max(ref)
+    gen_som_train(ref)
     gen_state_keys(ref)
     gen_classifier(ref, "classifier_b2_n256", 2, 256, "sampled", seed=1)
     gen_classifier(ref, "classifier_b2_n200_emptynodes", 2, 200, "uniform", seed=2)

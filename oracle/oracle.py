@@ -121,6 +121,57 @@ def canon_sets(min_idx, k):
     return torch.sort(min_idx.view(B, k, N).permute(0, 2, 1).long(), dim=2)[0]
 
 
+# ---- batch-SOM training (§8f-4) -------------------------------------------------------------------
+def som_init_weighting_matrix(rows, cols, sigma=0.4):
+    """BatchSOM.gaussian / get_init_weighting_matrix, util/som.py:214-229 -> [M, rows, cols]."""
+    d = 2 * np.pi * sigma * sigma
+    w = torch.empty(rows * cols, rows, cols)
+    for idx in range(rows * cols):
+        i, j = idx // cols, idx % cols
+        ax = np.exp(-np.power(np.arange(rows) - i, 2) / d)
+        ay = np.exp(-np.power(np.arange(cols) - j, 2) / d)
+        w[idx] = torch.from_numpy(np.outer(ax, ay).astype(np.float32))
+    return w
+
+
+def som_batch_update(node, x, init_w, learning_rate, sigma, sigma0=0.4):
+    """BatchSOM.batch_update, util/som.py:295-347, with the same ATen ops. node [B,3,M] (a new
+    tensor is returned), x [B,3,N], init_w [M,rows,cols]."""
+    B, C, N = x.shape
+    M, rows, cols = init_w.shape
+    node_e = node.unsqueeze(2).expand(B, C, N, M)                               # :301
+    x_e = x.unsqueeze(3).expand_as(node_e)
+    diff_norm = ((x_e - node_e) ** 2).sum(dim=1)                                # :305-306
+    _, min_idx = torch.min(diff_norm, dim=2)                                    # :309
+    ids = torch.arange(M, dtype=torch.int64).view(1, 1, M)
+    mask = torch.eq(min_idx.unsqueeze(2).expand(B, N, M), ids).float()          # :310-314
+    mask_row_sum = torch.sum(mask, dim=1) + 0.00001                             # :315
+    mask_row_max, _ = torch.max(mask, dim=1)                                    # :316
+    masked_sum = torch.sum(x_e * mask.unsqueeze(1).expand_as(x_e), dim=2)       # :319-320
+    mean = masked_sum / mask_row_sum.unsqueeze(1).expand_as(masked_sum)         # :321-322
+    mean_e = mean.unsqueeze(3).expand(B, C, M, M)                               # :326-328
+    diff = mean_e - node.unsqueeze(2).expand_as(mean_e)                         # :329-330
+    diff = diff * mask_row_max.unsqueeze(2).unsqueeze(1).expand_as(diff)        # :331
+    scale = 1.0 / ((sigma / sigma0) ** 2)                                       # :232-235
+    W = torch.exp(torch.log(init_w) * scale)
+    W = W.unsqueeze(0).unsqueeze(1).expand(B, C, M, rows, cols)                 # :337-342
+    delta = (diff.view(B, C, M, rows, cols) * W * learning_rate).sum(dim=2)     # :343-347
+    return (node.view(B, C, rows, cols) + delta).view(B, C, M), min_idx
+
+
+def som_optimize(x, node_init_value, rows, cols, lr0=0.5, sigma0=0.4, max_iteration=60):
+    """BatchSOM.optimize, util/som.py:352-366. node_init_value [3,M] (the potential-field start,
+    which tests take from the golden file — it is numpy-RNG-seeded host preprocessing)."""
+    init_w = som_init_weighting_matrix(rows, cols, sigma0)
+    node = node_init_value.unsqueeze(0).expand(x.shape[0], -1, -1).contiguous()
+    for _ in range(int(max_iteration / 3)):
+        node, _ = som_batch_update(node, x, init_w, lr0, sigma0, sigma0)
+    for it in range(max_iteration):
+        node, _ = som_batch_update(node, x, init_w, lr0 / (1 + 2 * it / max_iteration),
+                                   sigma0 / (1 + 2 * it / max_iteration), sigma0)
+    return node
+
+
 # ---- layers (eval mode) -------------------------------------------------------------------------------
 def _bn(y, st, prefix):
     return F.batch_norm(y, st[prefix + ".running_mean"], st[prefix + ".running_var"],

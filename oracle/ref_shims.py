@@ -48,6 +48,23 @@ class _IndexFlatL2:
         return D.numpy(), I.numpy()
 
 
+class cpu_only:
+    """Context manager for constructing reference objects for the CPU arm on a machine that HAS a
+    GPU: util/som.py:188 picks `cuda:%d if torch.cuda.is_available() else cpu` for the SOM nodes
+    regardless of opt.device, which mixes devices when the model itself is on the CPU. Inside the
+    context torch.cuda.is_available() answers False (shim 4: an environment answer, the reference
+    code is untouched)."""
+
+    def __enter__(self):
+        self._orig = torch.cuda.is_available
+        torch.cuda.is_available = lambda: False
+        return self
+
+    def __exit__(self, *exc):
+        torch.cuda.is_available = self._orig
+        return False
+
+
 def install(use_ref_plugin=True, prefer_pyref=False, pool_threads=None):
     """Register the shims and put the reference on sys.path. Returns the reference's modules.
     pool_threads: when set, CPU tensors handed to index_max.forward_cuda go to the reference's

@@ -102,6 +102,31 @@ def som_mask(min_idx_i32, M):
     return mask
 
 
+def som_train(x, node_init, weights, lr, want_idx=False):
+    """T batch-SOM iterations in one launch (util/som.py:295-366). x [B,3,N]; node_init [3,M]
+    (shared) or [B,3,M]; weights [T,M,M]; lr [T] -> node [B,3,M] (and the last assignment
+    [B,N] i32)."""
+    _chk(x, "x", torch.float32)
+    _chk(node_init, "node_init", torch.float32)
+    _chk(weights, "weights", torch.float32)
+    _chk(lr, "lr", torch.float32)
+    B, C, N = x.shape
+    M = node_init.shape[-1]
+    T = weights.shape[0]
+    batched = node_init.dim() == 3
+    if C != 3 or node_init.shape[-2] != 3 or (batched and node_init.shape[0] != B) \
+            or tuple(weights.shape[1:]) != (M, M) or lr.numel() != T:
+        raise RuntimeError("som_train: expected x [B,3,N], node_init [3,M]|[B,3,M], weights [T,M,M], "
+                           "lr [T]; got %s %s %s %s" % (tuple(x.shape), tuple(node_init.shape),
+                                                        tuple(weights.shape), tuple(lr.shape)))
+    with torch.cuda.device(x.device):
+        out = torch.empty((B, 3, M), dtype=torch.float32, device=x.device)
+        idx = torch.empty((B, N), dtype=torch.int32, device=x.device) if want_idx else None
+        _call("sonet_som_train", _C.ptr(x), _C.ptr(node_init), int(batched), _C.ptr(weights),
+              _C.ptr(lr), T, B, N, M, _C.ptr(out), _C.ptr(idx), _stream(x))
+    return (out, idx) if want_idx else out
+
+
 def som_decenter(x, sn, cluster_mean, min_idx_i32, k, want_centers=False):
     """-> (x_aug [B,3(+3),kN], centers [B,3,kN] or None)."""
     _chk(x, "x", torch.float32)

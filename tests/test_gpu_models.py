@@ -187,6 +187,8 @@ def test_cfg2_benchmarked_pipeline_vs_oracle(oracle_mod):
     for i, (seed, mode) in enumerate(((61, "sampled"), (62, "sampled"), (63, "sampled"),
                                       (64, "uniform"))):
         inp = synth.synth_inputs(B, N, seed=seed, node_mode=mode)
+        if mode == "uniform":
+            inp["node"] = inp["node"] * 2.5     # nodes far outside the cloud: many stay empty
         m.set_input(*[inp[k] for k in keys])
         m.test_model()
         if i in (1, 2):

@@ -86,3 +86,27 @@ def test_topk_c_restatement_matches_aten_expression(oracle_mod):
     assert torch.equal(got, dist.view(2, 3, 333).permute(0, 2, 1))
     want = torch.topk(d, 3, dim=2, largest=False, sorted=True)[0]
     assert torch.equal(got, want)
+
+
+def test_som_training_oracle_vs_reference(oracle_mod):
+    """§8f-4: the oracle restatement of BatchSOM.batch_update / optimize (util/som.py:295-366)
+    against what the reference itself produced (bit-exact: same ATen ops)."""
+    g = golden("som_train")
+    x = torch.from_numpy(g["x"])
+    ni = torch.from_numpy(g["node_init_value"])
+    init_w = oracle_mod.som_init_weighting_matrix(8, 8)
+    n0 = ni.unsqueeze(0).expand(x.shape[0], -1, -1).contiguous()
+    n1, _ = oracle_mod.som_batch_update(n0, x, init_w, 0.5, 0.4)
+    n2, _ = oracle_mod.som_batch_update(n1, x, init_w, 0.31, 0.22)
+    assert_close(n1, g["node_after_1"], "batch_update 1", 1e-6)
+    assert_close(n2, g["node_after_2"], "batch_update 2", 1e-6)
+    assert_close(oracle_mod.som_optimize(x, ni, 8, 8), g["node_optimized"], "optimize", 1e-5)
+
+
+def test_potential_field_start_matches_reference():
+    """BatchSOM.node_init_value (util/som.py:203-206, util/potential_field.py) restated in
+    vectorised numpy: bit-equal after the reference's float32 cast."""
+    from sonet_b200 import som
+    g = golden("som_train")
+    s = som.BatchSOM(8, 8, 3, 0, 2)
+    assert np.array_equal(s.node_init_value.numpy(), g["node_init_value"])
