@@ -116,6 +116,25 @@ int sonet_som_train(const float* x, const float* node_init, int node_init_batche
                     const float* weights, const float* lr, int T, int B, int N, int M,
                     float* node_out, int32_t* last_idx, sonet_stream_t stream);
 
+/* ---- f-3: on-device training augmentation of a batch ----------------------------------------------
+ * Replaces the per-item numpy pipeline of the loader (data/modelnet_shrec_loader.py:218-247 over
+ * data/augmentation.py:52-144) for all clouds at once: pc, sn [B,3,N] and som [B,3,M] (each
+ * nullable together with its output) go through
+ *   v = v . rot1[b] ; v = v . rot2[b]     rot1/rot2 [B,3,3] f64 row-major, nullable (identity)
+ *   v += clip(sigma * g, -clip, clip)     per array (sigma <= 0: no jitter)
+ *   v *= scale[b]                         [B] f64, nullable
+ *   v += shift[b]                         [B,3] f64, nullable; points and SOM nodes only
+ * in float64 like the loader, rounded to float32 once. The standard-normal draws g are either
+ * given (noise_* [B,P,3] f64, DEVICE pointers: the loader's own numpy stream -> reproduces it) or,
+ * when the pointer is NULL, generated in the kernel by Philox4x32-10 + Box-Muller keyed by
+ * (seed, cloud, array, point). All matrices/vectors are device pointers. */
+int sonet_augment_f32(const float* pc, const float* sn, const float* som, int B, int N, int M,
+                      const double* rot1, const double* rot2, const double* scale,
+                      const double* shift, double sigma_pc, double clip_pc, double sigma_sn,
+                      double clip_sn, double sigma_som, double clip_som, const double* noise_pc,
+                      const double* noise_sn, const double* noise_som, unsigned long long seed,
+                      float* pc_out, float* sn_out, float* som_out, sonet_stream_t stream);
+
 /* ---- a-4/a-5/a-8/a-9/a-10: point-wise shared MLP layer (1x1 conv + folded BN + ReLU) ---------
  * Replaces EquivariantLayer.forward / MyConv2d(1x1).forward in eval mode
  * (models/layers.py:203-210, 282-296): out[b,co,p] = act(scale[co]*sum_ci W[co,ci]*X[b,ci,p] +

@@ -230,6 +230,47 @@ def gen_som_train(ref):
     print("som_train.npz: reference BatchSOM == oracle restatement (bit-exact)")
 
 
+def gen_augment(ref):
+    """§8f-3: the loader's augmentation tail (data/modelnet_shrec_loader.py:218-247) executed with
+    the REFERENCE's own data/augmentation.py functions on seeded clouds, numpy global RNG seeded —
+    the fixture the on-device augmentation must reproduce from the same seed."""
+    import importlib
+    aug = importlib.import_module("data.augmentation")          # the reference's module
+    rs = np.random.RandomState(31)
+    B, N, M = 3, 257, 64
+    pc = rs.uniform(-1, 1, size=(B, N, 3)).astype(np.float32)
+    sn = rs.normal(size=(B, N, 3)).astype(np.float32)
+    sn /= np.linalg.norm(sn, axis=2, keepdims=True)
+    som = rs.uniform(-1, 1, size=(B, M, 3)).astype(np.float32)
+    out = dict(pc=pc.transpose(0, 2, 1).copy(), sn=sn.transpose(0, 2, 1).copy(),
+               som=som.transpose(0, 2, 1).copy(), np_seed=np.int64(4242))
+    for tag, (rh, rp, tp) in {"all": (True, True, True), "plain": (False, False, False)}.items():
+        np.random.seed(4242)
+        res = [[], [], []]
+        for b in range(B):                                        # loader :224-247, verbatim order
+            pc_np, sn_np, som_np = pc[b], sn[b], som[b]
+            if rh:
+                pc_np, sn_np, som_np = aug.rotate_point_cloud_with_normal_som(pc_np, sn_np, som_np)
+            if rp:
+                pc_np, sn_np, som_np = aug.rotate_perturbation_point_cloud_with_normal_som(
+                    pc_np, sn_np, som_np)
+            pc_np = aug.jitter_point_cloud(pc_np)
+            sn_np = aug.jitter_point_cloud(sn_np)
+            som_np = aug.jitter_point_cloud(som_np, sigma=0.04, clip=0.1)
+            scale = np.random.uniform(low=0.8, high=1.2)
+            pc_np, som_np, sn_np = pc_np * scale, som_np * scale, sn_np * scale
+            if tp:
+                shift = np.random.uniform(-0.1, 0.1, (1, 3))
+                pc_np += shift
+                som_np += shift
+            for lst, a in zip(res, (pc_np, sn_np, som_np)):
+                lst.append(a.transpose().astype(np.float32))      # loader :250-256
+        out[tag + "_pc"], out[tag + "_sn"], out[tag + "_som"] = (np.stack(r) for r in res)
+    np.random.seed()
+    np.savez_compressed(os.path.join(GOLDEN, "augment.npz"), **out)
+    print("wrote augment.npz")
+
+
 def gen_state_keys(ref):
     """Names and shapes of every state_dict tensor of the reference networks (checkpoint
     compatibility contract, SURVEY.md §5 'Checkpoint / resume')."""
@@ -264,6 +305,7 @@ def main():
         return
     gen_index_max(ref)
     gen_som_train(ref)
+    gen_augment(ref)
     gen_state_keys(ref)
     gen_classifier(ref, "classifier_b2_n256", 2, 256, "sampled", seed=1)
     gen_classifier(ref, "classifier_b2_n200_emptynodes", 2, 200, "uniform", seed=2)

@@ -97,14 +97,21 @@ def som_topk(x, node, k):
     return idx, dist
 
 
-def query_topk(x, node, k):
+def query_topk(x, node, k, sorted_slots=False):
     """BatchSOM.query_topk, util/som.py:237-269, with the same ATen ops -> (mask [B,kN,M] int32,
-    mask_row_max [B,M] int32, min_idx [B,kN] int64)."""
+    mask_row_max [B,M] int32, min_idx [B,kN] int64).
+
+    sorted_slots: the reference calls topk(sorted=False), whose slot order is implementation
+    defined (it differs between torch's CPU and CUDA kernels and between sizes). The order only
+    matters through one quirk: an EMPTY node gathers "the feature of stacked copy 0"
+    (models/networks.py:185), i.e. of point 0 decentred by whatever node topk put in slot 0.
+    sorted_slots=True picks the instance "slot order = ascending distance" — the order the CUDA
+    path emits — so that tensors downstream of empty nodes can be compared exactly."""
     M = node.shape[2]
     node_e = node.unsqueeze(2).expand(x.size(0), x.size(1), x.size(2), M)
     diff = x.unsqueeze(3).expand_as(node_e) - node_e
     diff_norm = (diff ** 2).sum(dim=1)
-    _, min_idx = torch.topk(diff_norm, k=k, dim=2, largest=False, sorted=False)   # B,N,k
+    _, min_idx = torch.topk(diff_norm, k=k, dim=2, largest=False, sorted=bool(sorted_slots))   # B,N,k
     ids = torch.arange(M, dtype=torch.int64).view(1, 1, M, 1)
     mask = torch.eq(min_idx.unsqueeze(2).expand(-1, -1, M, -1), ids).int()        # B,N,M,k
     mask = torch.cat([mask[..., i] for i in range(k)], dim=1)                      # B,kN,M
@@ -256,13 +263,13 @@ def knn_module(coord, x, knn_I, K, center_type, st, prefix):
 
 
 # ---- networks -----------------------------------------------------------------------------------------
-def encoder_forward(st, opt, x, sn, node, node_knn_I, fast_pool=False):
+def encoder_forward(st, opt, x, sn, node, node_knn_I, fast_pool=False, sorted_slots=False):
     """Encoder.forward, models/networks.py:111-199 (eval mode). Returns a dict of every cached
     attribute. `st` = encoder state_dict. fast_pool: use the fastest CPU index_max (baseline
     timing) instead of the single-thread restatement."""
     k = opt.k
     M = node.shape[2]
-    mask, mask_row_max, min_idx = query_topk(x, node, k)                    # networks.py:127
+    mask, mask_row_max, min_idx = query_topk(x, node, k, sorted_slots)      # networks.py:127
     mask_row_sum = torch.sum(mask, dim=1)                                   # :128
     maskf = mask.unsqueeze(1).float()
     x_stack = torch.cat((x,) * k, dim=2)                                    # :132-137

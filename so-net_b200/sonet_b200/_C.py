@@ -27,6 +27,10 @@ _SIGNATURES = {
     "sonet_som_mask": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "sonet_som_train": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                         c_void_p, c_void_p, c_void_p],
+    "sonet_augment_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                          c_void_p, c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                          ctypes.c_double, ctypes.c_double, ctypes.c_double, c_void_p, c_void_p,
+                          c_void_p, ctypes.c_ulonglong, c_void_p, c_void_p, c_void_p, c_void_p],
     "sonet_som_decenter": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                            c_void_p, c_void_p, c_void_p],
     "sonet_pointwise_layer_f32": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,

@@ -127,6 +127,37 @@ def som_train(x, node_init, weights, lr, want_idx=False):
     return (out, idx) if want_idx else out
 
 
+def augment(pc, sn, som, rot1=None, rot2=None, scale=None, shift=None, jitter_pc=(0.0, 1.0),
+            jitter_sn=(0.0, 1.0), jitter_som=(0.0, 1.0), noise_pc=None, noise_sn=None,
+            noise_som=None, seed=0):
+    """One-launch batch augmentation (csrc/augment.cu). pc, sn [B,3,N], som [B,3,M] f32 (sn / som
+    may be None); rot1/rot2 [B,3,3], scale [B], shift [B,3], noise_* [B,P,3]: float64 device
+    tensors or None. jitter_* = (sigma, clip). -> (pc', sn', som')."""
+    _chk(pc, "pc", torch.float32)
+    _chk(sn, "sn", torch.float32, optional=True)
+    _chk(som, "som", torch.float32, optional=True)
+    for t, n in ((rot1, "rot1"), (rot2, "rot2"), (scale, "scale"), (shift, "shift"),
+                 (noise_pc, "noise_pc"), (noise_sn, "noise_sn"), (noise_som, "noise_som")):
+        _chk(t, n, torch.float64, optional=True)
+    B, _, N = pc.shape
+    M = 0 if som is None else som.shape[2]
+    for t, shp, n in ((rot1, (B, 3, 3), "rot1"), (rot2, (B, 3, 3), "rot2"), (scale, (B,), "scale"),
+                      (shift, (B, 3), "shift"), (noise_pc, (B, N, 3), "noise_pc"),
+                      (noise_sn, (B, N, 3), "noise_sn"), (noise_som, (B, M, 3), "noise_som")):
+        if t is not None and tuple(t.shape) != shp:
+            raise RuntimeError("augment: %s must have shape %s, got %s" % (n, shp, tuple(t.shape)))
+    with torch.cuda.device(pc.device):
+        po = torch.empty_like(pc)
+        so = torch.empty_like(sn) if sn is not None else None
+        mo = torch.empty_like(som) if som is not None else None
+        _call("sonet_augment_f32", _C.ptr(pc), _C.ptr(sn), _C.ptr(som), B, N, M, _C.ptr(rot1),
+              _C.ptr(rot2), _C.ptr(scale), _C.ptr(shift), float(jitter_pc[0]), float(jitter_pc[1]),
+              float(jitter_sn[0]), float(jitter_sn[1]), float(jitter_som[0]), float(jitter_som[1]),
+              _C.ptr(noise_pc), _C.ptr(noise_sn), _C.ptr(noise_som), int(seed) & (2 ** 64 - 1),
+              _C.ptr(po), _C.ptr(so), _C.ptr(mo), _stream(pc))
+    return po, so, mo
+
+
 def som_decenter(x, sn, cluster_mean, min_idx_i32, k, want_centers=False):
     """-> (x_aug [B,3(+3),kN], centers [B,3,kN] or None)."""
     _chk(x, "x", torch.float32)

@@ -144,8 +144,12 @@ def test_ctypes_arity_matches_the_header_prototypes():
         for q, ct in zip(plist, sig):           # and the same machine type, parameter by parameter
             if "*" in q or "sonet_stream_t" in q:
                 want = ctypes.c_void_p
+            elif "unsigned long long" in q:
+                want = ctypes.c_ulonglong
             elif "long long" in q:
                 want = ctypes.c_longlong
+            elif re.match(r"(const\s+)?double\b", q):
+                want = ctypes.c_double
             elif re.match(r"(const\s+)?float\b", q):
                 want = ctypes.c_float
             else:
