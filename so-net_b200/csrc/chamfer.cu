@@ -2,64 +2,153 @@
 //
 // Replaces ChamferLoss.forward (models/losses.py:237-290): the reference does, per cloud, two
 // Faiss IndexFlatL2 builds + two k=1 searches through host numpy (losses.py:247-276), then
-// robust_norm = sqrt(sum_c d_c^2 + 1e-8) (losses.py:17-27) and means. Here the whole batch is
-// three launches with no host round trip:
-//   nn_kernel       thread per query point, database tiled through shared memory (float4 per
-//                   point, broadcast reads), exact direct-difference distance
-//                   ((dx*dx+dy*dy)+dz*dz, no FMA), strict '<' over ascending index = lowest
-//                   index on ties; emits the arg-min and sqrt(dmin + 1e-8).
-//   reduce kernels  fixed-order tree sums -> per-cloud means and the three scalar losses
-//                   (deterministic, independent of batch sharding).
-// The search is FP32-ALU bound (arithmetic intensity >> 100 flop/B), not HBM bound.
+// robust_norm = sqrt(sum_c d_c^2 + 1e-8) (losses.py:17-27) and means. Here the whole batch runs
+// with no host round trip, and BOTH directions come from ONE evaluation of each (pred, gt) pair:
+//
+//   chamfer_pair_kernel   a warp owns 256 gt points (8 per lane, in registers) and streams a tile
+//       of pred points from shared memory (broadcast LDS.128). Every squared distance is computed
+//       once — exact direct differences, ((dx*dx+dy*dy)+dz*dz) with separate roundings, the
+//       arithmetic of the brute-force oracle — and feeds the running minimum of its gt point
+//       (in-register FMNMX) and of its pred point (in-thread FMNMX over the lane's 8 columns, one
+//       REDUX.MIN across the warp, lane r%32 keeps row r). Non-negative floats order like their
+//       bit patterns, so the cross-warp / cross-CTA combination is an unsigned atomicMin
+//       (shared memory first, then one RED per row and CTA) straight into the caller's
+//       elem_fwd / elem_bwd arrays.
+//   The eval-mode loss needs only the minimum DISTANCES: sqrt(dmin + 1e-8) is the same number
+//   whichever of several equidistant neighbours is selected. The arg-min indices (training:
+//   the differentiable gather of losses.py:269,276) come from a second pass of the same kernel
+//   that looks for the LOWEST index attaining the final minimum — the oracle's strict-'<'
+//   ascending-scan tie rule — so indices stay bit-identical to the brute-force search.
+//   chamfer_cloud/final   sqrt(d + 1e-8) in place, fixed-order tree sums -> per-cloud means and the
+//       three scalar losses (deterministic, independent of batch sharding).
+// Bound: FP32 ALU / issue (arithmetic intensity >> 100 flop/B): 8 FP + 2 FMNMX + ~0.4 per pair.
 #include <algorithm>
 
 #include "common.cuh"
 
 namespace sonet {
 
-constexpr int NN_THREADS = 256;
-constexpr int NN_TILE = 1024;
+constexpr int CH_WARPS = 4;            // warps per CTA, each with its own 256-column chunk
+constexpr int CH_RN = 8;               // gt points per lane
+constexpr int CH_COLS = 32 * CH_RN;    // 256 columns per warp
+constexpr int CH_TM = 256;             // pred points per CTA tile
+constexpr float CH_FAR = 1.0e30f;      // padding coordinate: (x - 1e30)^2 overflows to +inf
 
-__global__ void __launch_bounds__(NN_THREADS)
-    nn_kernel(const float* __restrict__ query, int Q, const float* __restrict__ db, int D,
-              int32_t* __restrict__ out_idx, float* __restrict__ out_elem) {
-  __shared__ float4 tile[NN_TILE];
-  const int b = blockIdx.y;
-  const float* qb = query + static_cast<size_t>(b) * 3 * Q;
-  const float* dbb = db + static_cast<size_t>(b) * 3 * D;
-  const int q = blockIdx.x * NN_THREADS + threadIdx.x;
-  const bool live = q < Q;
-  float px = 0.f, py = 0.f, pz = 0.f;
-  if (live) {
-    px = qb[q];
-    py = qb[Q + q];
-    pz = qb[2 * Q + q];
+// row_key [B,Mp] / col_key [B,N]: running minima as float bit patterns (init 0xFFFFFFFF).
+// IDX pass: row_key/col_key hold the FINAL minima; row_idx/col_idx (init INT_MAX-like) receive the
+// lowest index attaining them.
+template <bool IDX>
+__global__ void __launch_bounds__(CH_WARPS * 32)
+    chamfer_pair_kernel(const float* __restrict__ pred, int Mp, const float* __restrict__ gt, int N,
+                        unsigned* __restrict__ row_key, unsigned* __restrict__ col_key,
+                        int* __restrict__ row_idx, int* __restrict__ col_idx) {
+  __shared__ float4 srow[CH_TM];
+  __shared__ unsigned srmin[CH_TM];    // value pass: row minima of this CTA; idx pass: row arg-min
+  __shared__ float srfin[IDX ? CH_TM : 1];
+  __shared__ int done;                 // warps of this CTA that finished their columns
+  const int b = blockIdx.z;
+  const int m0 = blockIdx.y * CH_TM;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n0 = (blockIdx.x * CH_WARPS + warp) * CH_COLS;
+  const float* pb = pred + static_cast<size_t>(b) * 3 * Mp;
+  const float* gb = gt + static_cast<size_t>(b) * 3 * N;
+  const int rows = min(CH_TM, Mp - m0);
+  for (int i = threadIdx.x; i < CH_TM; i += CH_WARPS * 32) {
+    const int m = m0 + i;
+    srow[i] = (m < Mp) ? make_float4(pb[m], pb[Mp + m], pb[2 * Mp + m], 0.f)
+                       : make_float4(CH_FAR, CH_FAR, CH_FAR, 0.f);
+    srmin[i] = IDX ? 0x7fffffffu : 0xffffffffu;
+    if (IDX) srfin[i] = (m < Mp) ? __uint_as_float(row_key[static_cast<size_t>(b) * Mp + m]) : -1.f;
   }
-  float best = __int_as_float(0x7f800000);
-  int bi = 0;
-  for (int d0 = 0; d0 < D; d0 += NN_TILE) {
-    const int cnt = min(NN_TILE, D - d0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < cnt; i += NN_THREADS)
-      tile[i] = make_float4(dbb[d0 + i], dbb[D + d0 + i], dbb[2 * D + d0 + i], 0.f);
-    __syncthreads();
-    if (live) {
-#pragma unroll 8
-      for (int i = 0; i < cnt; ++i) {
-        const float4 t = tile[i];
-        const float dx = __fsub_rn(px, t.x), dy = __fsub_rn(py, t.y), dz = __fsub_rn(pz, t.z);
-        const float d =
-            __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        if (d < best) {
-          best = d;
-          bi = d0 + i;
+  if (threadIdx.x == 0) done = 0;
+  __syncthreads();
+  if (n0 >= N) return;                 // (after the only CTA-wide barrier but the last)
+
+  float gx[CH_RN], gy[CH_RN], gz[CH_RN], cmin[CH_RN];
+  int cidx[CH_RN];
+#pragma unroll
+  for (int j = 0; j < CH_RN; ++j) {
+    const int n = n0 + j * 32 + lane;
+    const bool ok = n < N;
+    gx[j] = ok ? gb[n] : -CH_FAR;
+    gy[j] = ok ? gb[N + n] : -CH_FAR;
+    gz[j] = ok ? gb[2 * N + n] : -CH_FAR;
+    if (IDX) {
+      cmin[j] = ok ? __uint_as_float(col_key[static_cast<size_t>(b) * N + n]) : -1.f;  // final
+      cidx[j] = 0x7fffffff;
+    } else {
+      cmin[j] = __int_as_float(0x7f800000);
+    }
+  }
+
+  const int row_blocks = (rows + 31) >> 5;
+  for (int rb = 0; rb < row_blocks; ++rb) {
+    unsigned keep = IDX ? 0x7fffffffu : 0xffffffffu;   // row (rb*32 + lane): min / arg-min so far
+#pragma unroll 4
+    for (int ri = 0; ri < 32; ++ri) {
+      const int r = rb * 32 + ri;
+      const float4 p = srow[r];
+      if (!IDX) {
+        float rmin = __int_as_float(0x7f800000);
+#pragma unroll
+        for (int j = 0; j < CH_RN; ++j) {
+          const float dx = __fsub_rn(p.x, gx[j]), dy = __fsub_rn(p.y, gy[j]), dz = __fsub_rn(p.z, gz[j]);
+          const float d =
+              __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+          cmin[j] = fminf(cmin[j], d);
+          rmin = fminf(rmin, d);
         }
+        const unsigned red = __reduce_min_sync(0xffffffffu, __float_as_uint(rmin));
+        if (lane == ri) keep = red;
+      } else {
+        const float rf = srfin[r];
+        int cand = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < CH_RN; ++j) {
+          const float dx = __fsub_rn(p.x, gx[j]), dy = __fsub_rn(p.y, gy[j]), dz = __fsub_rn(p.z, gz[j]);
+          const float d =
+              __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+          if (d == cmin[j]) cidx[j] = min(cidx[j], m0 + r);          // lowest pred index
+          if (d == rf) cand = min(cand, n0 + j * 32 + lane);         // lowest gt index
+        }
+        const unsigned red = __reduce_min_sync(0xffffffffu, static_cast<unsigned>(cand));
+        if (lane == ri) keep = red;
+      }
+    }
+    atomicMin(&srmin[rb * 32 + lane], keep);
+  }
+
+  // columns: complete over this CTA's pred tile -> one RED per column (a plain store would do
+  // when Mp <= CH_TM, but the RED keeps one code path)
+#pragma unroll
+  for (int j = 0; j < CH_RN; ++j) {
+    const int n = n0 + j * 32 + lane;
+    if (n < N) {
+      if (IDX) {
+        if (cidx[j] != 0x7fffffff) atomicMin(col_idx + static_cast<size_t>(b) * N + n, cidx[j]);
+      } else {
+        atomicMin(col_key + static_cast<size_t>(b) * N + n, __float_as_uint(cmin[j]));
       }
     }
   }
-  if (live) {
-    if (out_idx) out_idx[static_cast<size_t>(b) * Q + q] = bi;
-    out_elem[static_cast<size_t>(b) * Q + q] = __fsqrt_rn(__fadd_rn(best, 1e-8f));
+  // rows: combined across this CTA's warps in shared memory; the LAST warp to get here flushes.
+  // (warps that returned early never touch srmin; count only the live ones)
+  __syncwarp();
+  __threadfence_block();
+  const int live_warps = min(CH_WARPS, (N - blockIdx.x * CH_WARPS * CH_COLS + CH_COLS - 1) / CH_COLS);
+  int ticket = 0;
+  if (lane == 0) ticket = atomicAdd(&done, 1);
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  if (ticket == live_warps - 1) {
+    __threadfence_block();
+    for (int i = lane; i < rows; i += 32) {
+      const unsigned v = srmin[i];
+      if (IDX) {
+        if (v != 0x7fffffffu) atomicMin(row_idx + static_cast<size_t>(b) * Mp + m0 + i, static_cast<int>(v));
+      } else {
+        atomicMin(row_key + static_cast<size_t>(b) * Mp + m0 + i, v);
+      }
+    }
   }
 }
 
@@ -75,17 +164,27 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
   return r;
 }
 
-// grid = B: per-cloud means of the two directions
+// grid = B: keys (min squared distances) -> sqrt(d + 1e-8) in place, per-cloud means
 __global__ void __launch_bounds__(256)
-    chamfer_cloud_kernel(const float* __restrict__ elem_fwd, int Mp, const float* __restrict__ elem_bwd,
-                         int N, float* __restrict__ fwd_arr, float* __restrict__ bwd_arr) {
+    chamfer_cloud_kernel(float* __restrict__ elem_fwd, int Mp, float* __restrict__ elem_bwd, int N,
+                         float* __restrict__ fwd_arr, float* __restrict__ bwd_arr) {
   __shared__ float red[256];
   const int b = blockIdx.x;
   float s = 0.f;
-  for (int i = threadIdx.x; i < Mp; i += 256) s += elem_fwd[static_cast<size_t>(b) * Mp + i];
+  for (int i = threadIdx.x; i < Mp; i += 256) {
+    float* p = elem_fwd + static_cast<size_t>(b) * Mp + i;
+    const float e = __fsqrt_rn(__fadd_rn(*p, 1e-8f));
+    *p = e;
+    s += e;
+  }
   const float f = block_sum_256(s, red);
   s = 0.f;
-  for (int i = threadIdx.x; i < N; i += 256) s += elem_bwd[static_cast<size_t>(b) * N + i];
+  for (int i = threadIdx.x; i < N; i += 256) {
+    float* p = elem_bwd + static_cast<size_t>(b) * N + i;
+    const float e = __fsqrt_rn(__fadd_rn(*p, 1e-8f));
+    *p = e;
+    s += e;
+  }
   const float g = block_sum_256(s, red);
   if (threadIdx.x == 0) {
     fwd_arr[b] = __fdiv_rn(f, static_cast<float>(Mp));
@@ -122,11 +221,28 @@ extern "C" int sonet_chamfer_f32(const float* pred, const float* gt, int B, int 
   SONET_REQUIRE(B <= 65535, "chamfer: B=%d exceeds grid limit", B);
   SONET_REQUIRE(pred && gt && elem_fwd && elem_bwd && loss_fwd_arr && loss_bwd_arr && loss,
                 "chamfer: null pointer");
+  SONET_REQUIRE((idx_fwd == nullptr) == (idx_bwd == nullptr),
+                "chamfer: idx_fwd and idx_bwd go together");
   cudaStream_t st = as_stream(stream);
-  nn_kernel<<<dim3((Mp + NN_THREADS - 1) / NN_THREADS, B), NN_THREADS, 0, st>>>(pred, Mp, gt, N,
-                                                                                idx_fwd, elem_fwd);
-  nn_kernel<<<dim3((N + NN_THREADS - 1) / NN_THREADS, B), NN_THREADS, 0, st>>>(gt, N, pred, Mp,
-                                                                               idx_bwd, elem_bwd);
+  // the element arrays double as the running minima (uint keys of non-negative floats)
+  cudaMemsetAsync(elem_fwd, 0xff, sizeof(float) * static_cast<size_t>(B) * Mp, st);
+  cudaMemsetAsync(elem_bwd, 0xff, sizeof(float) * static_cast<size_t>(B) * N, st);
+  const dim3 grid((N + CH_WARPS * CH_COLS - 1) / (CH_WARPS * CH_COLS), (Mp + CH_TM - 1) / CH_TM, B);
+  SONET_REQUIRE(grid.y <= 65535, "chamfer: Mp=%d exceeds grid limit", Mp);
+  chamfer_pair_kernel<false><<<grid, CH_WARPS * 32, 0, st>>>(
+      pred, Mp, gt, N, reinterpret_cast<unsigned*>(elem_fwd), reinterpret_cast<unsigned*>(elem_bwd),
+      nullptr, nullptr);
+  int rc = check_launch("chamfer(pairs)");
+  if (rc) return rc;
+  if (idx_fwd) {
+    cudaMemsetAsync(idx_fwd, 0x7f, sizeof(int32_t) * static_cast<size_t>(B) * Mp, st);
+    cudaMemsetAsync(idx_bwd, 0x7f, sizeof(int32_t) * static_cast<size_t>(B) * N, st);
+    chamfer_pair_kernel<true><<<grid, CH_WARPS * 32, 0, st>>>(
+        pred, Mp, gt, N, reinterpret_cast<unsigned*>(elem_fwd), reinterpret_cast<unsigned*>(elem_bwd),
+        idx_fwd, idx_bwd);
+    rc = check_launch("chamfer(arg-min)");
+    if (rc) return rc;
+  }
   chamfer_cloud_kernel<<<B, 256, 0, st>>>(elem_fwd, Mp, elem_bwd, N, loss_fwd_arr, loss_bwd_arr);
   chamfer_final_kernel<<<1, 256, 0, st>>>(loss_fwd_arr, loss_bwd_arr, B, loss);
   return check_launch("chamfer");

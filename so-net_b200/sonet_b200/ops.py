@@ -11,7 +11,7 @@ from . import _C
 
 LAUNCHES = 0          # C-ABI compute calls issued
 KERNEL_LAUNCHES = 0   # CUDA kernels launched by those calls (bench.py's gpu_launches)
-_KERNELS_PER_CALL = {"sonet_som_assign": 2, "sonet_chamfer_f32": 4}
+_KERNELS_PER_CALL = {"sonet_som_assign": 2, "sonet_chamfer_f32": 3}
 PROFILE = None        # when a list: every call appends (name, start_event, end_event)
 
 
@@ -309,7 +309,7 @@ def chamfer(pred, gt, want_idx=False):
         loss = torch.empty((3,), dtype=torch.float32, device=dev)
         _call("sonet_chamfer_f32", _C.ptr(pred), _C.ptr(gt), B, Mp, N, _C.ptr(idx_f),
               _C.ptr(idx_b), _C.ptr(ef), _C.ptr(eb), _C.ptr(fa), _C.ptr(ba), _C.ptr(loss),
-              _stream(pred))
+              _stream(pred), kernels=4 if want_idx else 3)
     return dict(loss=loss, fwd_arr=fa, bwd_arr=ba, elem_fwd=ef, elem_bwd=eb, idx_fwd=idx_f,
                 idx_bwd=idx_b)
 

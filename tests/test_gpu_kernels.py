@@ -262,6 +262,27 @@ def test_chamfer_vs_oracle(oracle_mod, B, Mp, N):
     assert_close(r["fwd_arr"] + r["bwd_arr"], want["loss_array"], "loss_array")
 
 
+def test_chamfer_ties_lowest_index_and_value_only_path(oracle_mod):
+    """Exact duplicates in both clouds: every query has several equidistant neighbours; the
+    arg-min pass must return the LOWEST index (the oracle's strict '<' ascending scan), and the
+    eval-mode value-only path must give bit-identical element losses."""
+    from sonet_b200 import ops
+    rs = np.random.RandomState(77)
+    a = rs.uniform(-1, 1, size=(2, 3, 300)).astype(np.float32)
+    g = rs.uniform(-1, 1, size=(2, 3, 700)).astype(np.float32)
+    pred = torch.from_numpy(np.concatenate([a, a[:, :, ::-1], a[:, :, :57]], axis=2).copy())   # 657
+    gt = torch.from_numpy(np.concatenate([g, g, g[:, :, 100:400]], axis=2).copy())              # 1700
+    want = oracle_mod.chamfer(pred, gt)
+    r = ops.chamfer(pred.to(DEV), gt.to(DEV), want_idx=True)
+    assert torch.equal(r["idx_fwd"].cpu().long(), want["idx_fwd"])
+    assert torch.equal(r["idx_bwd"].cpu().long(), want["idx_bwd"])
+    assert int(r["idx_fwd"].max()) < 700 and int(r["idx_bwd"].max()) < 300      # never the copies
+    v = ops.chamfer(pred.to(DEV), gt.to(DEV), want_idx=False)
+    for k in ("elem_fwd", "elem_bwd", "fwd_arr", "bwd_arr", "loss"):
+        assert torch.equal(v[k], r[k]), k
+    assert_close(v["loss"][2], want["loss"], "chamfer loss with ties")
+
+
 def test_chamfer_golden_and_properties():
     from sonet_b200 import losses, ops, synth
     g = golden("autoencoder_b2_n256")

@@ -57,6 +57,15 @@ for K in ${NCUB:-}; do
      -o $O/prof_${N}_$TAG -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_${N}_$TAG.log 2>&1
   tail -2 $O/ncu_${N}_$TAG.log
 done
+# NCUO: "op:kernel_regex" pairs captured from tools/profile_ops.py (standalone ops)
+for PAIR in ${NCUO:-}; do
+  OP=${PAIR%%:*}; K=${PAIR##*:}
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s ${NCUO_SKIP:-2} -c 1 \
+     -o $O/prof_${OP}_$TAG -f python tools/profile_ops.py --op $OP > $O/ncu_${OP}_$TAG.log 2>&1
+  tail -2 $O/ncu_${OP}_$TAG.log
+done
+# OPS: standalone ops timed with CUDA events (tools/profile_ops.py)
+for OP in ${OPS:-}; do python tools/profile_ops.py --op $OP --reps 6 2>&1 | tail -1; done
 if [ "${SANI:-0}" = "1" ]; then
   for TOOL in memcheck racecheck synccheck; do
     timeout 1200 compute-sanitizer --tool $TOOL --print-limit 20 python tools/profile_step.py --steps 1 --batch 2 --npts 5000 \
