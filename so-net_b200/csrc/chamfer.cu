@@ -6,7 +6,8 @@
 // with no host round trip, and BOTH directions come from ONE evaluation of each (pred, gt) pair:
 //
 //   chamfer_pair_kernel   a warp owns 256 gt points (8 per lane, in registers) and streams a tile
-//       of pred points from shared memory (broadcast LDS.128). Every squared distance is computed
+//       of pred points from shared memory (broadcast LDS). The arithmetic is packed two columns
+//       per instruction (FADD2/FMUL2, sm_100's f32x2 ops: IEEE rn per half). Every squared distance is computed
 //       once — exact direct differences, ((dx*dx+dy*dy)+dz*dz) with separate roundings, the
 //       arithmetic of the brute-force oracle — and feeds the running minimum of its gt point
 //       (in-register FMNMX) and of its pred point (in-thread FMNMX over the lane's 8 columns, one
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(CH_WARPS * 32)
     chamfer_pair_kernel(const float* __restrict__ pred, int Mp, const float* __restrict__ gt, int N,
                         unsigned* __restrict__ row_key, unsigned* __restrict__ col_key,
                         int* __restrict__ row_idx, int* __restrict__ col_idx) {
-  __shared__ float4 srow[CH_TM];
+  __shared__ float2 srow[CH_TM][4];    // (x,x) (y,y) (z,z) pad: LDS.128 + LDS.64 -> packed operands
   __shared__ unsigned srmin[CH_TM];    // value pass: row minima of this CTA; idx pass: row arg-min
   __shared__ float srfin[IDX ? CH_TM : 1];
   __shared__ int done;                 // warps of this CTA that finished their columns
@@ -55,8 +56,11 @@ __global__ void __launch_bounds__(CH_WARPS * 32)
   const int rows = min(CH_TM, Mp - m0);
   for (int i = threadIdx.x; i < CH_TM; i += CH_WARPS * 32) {
     const int m = m0 + i;
-    srow[i] = (m < Mp) ? make_float4(pb[m], pb[Mp + m], pb[2 * Mp + m], 0.f)
-                       : make_float4(CH_FAR, CH_FAR, CH_FAR, 0.f);
+    const float rx = (m < Mp) ? pb[m] : CH_FAR, ry = (m < Mp) ? pb[Mp + m] : CH_FAR,
+                rz = (m < Mp) ? pb[2 * Mp + m] : CH_FAR;
+    srow[i][0] = make_float2(rx, rx);
+    srow[i][1] = make_float2(ry, ry);
+    srow[i][2] = make_float2(rz, rz);
     srmin[i] = IDX ? 0x7fffffffu : 0xffffffffu;
     if (IDX) srfin[i] = (m < Mp) ? __uint_as_float(row_key[static_cast<size_t>(b) * Mp + m]) : -1.f;
   }
@@ -64,15 +68,23 @@ __global__ void __launch_bounds__(CH_WARPS * 32)
   __syncthreads();
   if (n0 >= N) return;                 // (after the only CTA-wide barrier but the last)
 
-  float gx[CH_RN], gy[CH_RN], gz[CH_RN], cmin[CH_RN];
+  // NEGATED gt coordinates, two columns per register pair: p - g == p + (-g) bit for bit, and the
+  // packed add.rn.f32x2 / mul.rn.f32x2 (sm_100 FADD2/FMUL2) round each half like the scalar op —
+  // half the issue slots for the same arithmetic (the kernel is issue-bound, not pipe-bound)
+  float2 ngx[CH_RN / 2], ngy[CH_RN / 2], ngz[CH_RN / 2];
+  float cmin[CH_RN];
   int cidx[CH_RN];
 #pragma unroll
   for (int j = 0; j < CH_RN; ++j) {
     const int n = n0 + j * 32 + lane;
     const bool ok = n < N;
-    gx[j] = ok ? gb[n] : -CH_FAR;
-    gy[j] = ok ? gb[N + n] : -CH_FAR;
-    gz[j] = ok ? gb[2 * N + n] : -CH_FAR;
+    const float vx = ok ? -gb[n] : CH_FAR, vy = ok ? -gb[N + n] : CH_FAR,
+                vz = ok ? -gb[2 * N + n] : CH_FAR;
+    if (j & 1) {
+      ngx[j >> 1].y = vx; ngy[j >> 1].y = vy; ngz[j >> 1].y = vz;
+    } else {
+      ngx[j >> 1].x = vx; ngy[j >> 1].x = vy; ngz[j >> 1].x = vz;
+    }
     if (IDX) {
       cmin[j] = ok ? __uint_as_float(col_key[static_cast<size_t>(b) * N + n]) : -1.f;  // final
       cidx[j] = 0x7fffffff;
@@ -87,16 +99,17 @@ __global__ void __launch_bounds__(CH_WARPS * 32)
 #pragma unroll 4
     for (int ri = 0; ri < 32; ++ri) {
       const int r = rb * 32 + ri;
-      const float4 p = srow[r];
+      const float2 px = srow[r][0], py = srow[r][1], pz = srow[r][2];
       if (!IDX) {
         float rmin = __int_as_float(0x7f800000);
 #pragma unroll
-        for (int j = 0; j < CH_RN; ++j) {
-          const float dx = __fsub_rn(p.x, gx[j]), dy = __fsub_rn(p.y, gy[j]), dz = __fsub_rn(p.z, gz[j]);
-          const float d =
-              __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-          cmin[j] = fminf(cmin[j], d);
-          rmin = fminf(rmin, d);
+        for (int j = 0; j < CH_RN / 2; ++j) {
+          const float2 dx = add2_rn(px, ngx[j]), dy = add2_rn(py, ngy[j]),
+                       dz = add2_rn(pz, ngz[j]);
+          const float2 d = sqsum3_rn(dx, dy, dz);
+          cmin[2 * j] = fminf(cmin[2 * j], d.x);
+          cmin[2 * j + 1] = fminf(cmin[2 * j + 1], d.y);
+          rmin = fminf(rmin, fminf(d.x, d.y));
         }
         const unsigned red = __reduce_min_sync(0xffffffffu, __float_as_uint(rmin));
         if (lane == ri) keep = red;
@@ -104,12 +117,14 @@ __global__ void __launch_bounds__(CH_WARPS * 32)
         const float rf = srfin[r];
         int cand = 0x7fffffff;
 #pragma unroll
-        for (int j = 0; j < CH_RN; ++j) {
-          const float dx = __fsub_rn(p.x, gx[j]), dy = __fsub_rn(p.y, gy[j]), dz = __fsub_rn(p.z, gz[j]);
-          const float d =
-              __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-          if (d == cmin[j]) cidx[j] = min(cidx[j], m0 + r);          // lowest pred index
-          if (d == rf) cand = min(cand, n0 + j * 32 + lane);         // lowest gt index
+        for (int j = 0; j < CH_RN / 2; ++j) {
+          const float2 dx = add2_rn(px, ngx[j]), dy = add2_rn(py, ngy[j]),
+                       dz = add2_rn(pz, ngz[j]);
+          const float2 d = sqsum3_rn(dx, dy, dz);
+          if (d.x == cmin[2 * j]) cidx[2 * j] = min(cidx[2 * j], m0 + r);        // lowest pred index
+          if (d.y == cmin[2 * j + 1]) cidx[2 * j + 1] = min(cidx[2 * j + 1], m0 + r);
+          if (d.x == rf) cand = min(cand, n0 + (2 * j) * 32 + lane);             // lowest gt index
+          if (d.y == rf) cand = min(cand, n0 + (2 * j + 1) * 32 + lane);
         }
         const unsigned red = __reduce_min_sync(0xffffffffu, static_cast<unsigned>(cand));
         if (lane == ri) keep = red;

@@ -53,12 +53,12 @@ def test_device_noise_statistics_and_determinism():
     assert not torch.equal(a[0], c[0])
     j = a[0].double()
     assert abs(float(j.mean())) < 2e-4 and abs(float(j.std()) - 0.01) < 2e-4
-    assert float(j.abs().max()) <= 0.05
+    assert float(j.abs().max()) <= float(np.float32(0.05))
     assert abs(float((j[0] * j[1]).mean())) < 1e-6                 # clouds are independent
     assert abs(float((j * a[1].double()).mean())) < 1e-6           # arrays are independent
     jn = a[1].double()                                             # clip at 2.5 sigma is visible
-    assert float(jn.abs().max()) == pytest.approx(0.025, abs=1e-9)
-    frac = float((jn.abs() >= 0.025 - 1e-12).double().mean())
+    assert float(jn.abs().max()) == pytest.approx(0.025, abs=1e-8)
+    frac = float((jn.abs() >= 0.025 - 1e-8).double().mean())
     assert abs(frac - 0.01242) < 2e-3                              # P(|g| > 2.5)
     # normality of the unclipped bulk: kurtosis of N(0,1) is 3
     z = j / 0.01
