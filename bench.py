@@ -1,26 +1,31 @@
-"""bench.py — headline benchmark of the SO-Net forward hot path on B200 (BASELINE.json metric).
+"""bench.py — benchmark of the SO-Net forward hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg2]
 
-A "step" is one eval-mode classifier forward (ModelNet40 shape: batch 64 per GPU, N=5000 points,
-8x8 SOM, k=3, som_k=9, fp32) over one batch of synthetic clouds. N>1: launched by torchrun, one
-rank per GPU, weights replicated, batch sharded (weak scaling), one NCCL all-gather of the logits
-per step inside the timed region. Rank 0 prints ONE JSON line.
+Default (--config cfg2, BASELINE.json configs[1], the headline): a "step" is one eval-mode
+classifier forward (ModelNet40 shape: batch 64 per GPU, N=5000 points, 8x8 SOM, k=3, som_k=9,
+fp32) over one batch of synthetic clouds. The other BASELINE.json configs emit the same JSON
+shape: cfg1 (classifier B=8 N=1024), cfg3 (ShapeNetPart segmenter forward + per-point logits,
+B=32 N=1024), cfg4 (auto-encoder forward + Chamfer, B=32 N=5000). N>1: launched by torchrun, one
+rank per GPU, weights replicated, batch sharded (weak scaling), one NCCL all-gather of the step's
+result rows per step inside the timed region (issued asynchronously: step i's gather completes
+under step i+1's forward; every gather is waited for inside a timed step). Rank 0 prints ONE JSON
+line.
 
   value     clouds/s with inputs resident in HBM (CUDA events per step, L2 flushed between steps,
             max over ranks)
-  e2e       the same metric through the public API classifier.Model.set_input()/test_model() with
-            pinned HOST buffers: every step copies its full inputs host->device and reads its
-            logits device->host inside the timed region (K steps = K H2D + K D2H). The loop is a
-            serving loop pipelined by call order only: set_input (async, double-buffered, copy
-            stream) + test_model + async D2H of step i+1 are issued before the host waits for the
-            logits of step i
+  e2e       the same metric through the public API Model.set_input()/test_model() with pinned
+            HOST buffers: every step copies its full inputs host->device and reads its result
+            device->host inside the timed region (K steps = K H2D + K D2H). The loop is a serving
+            loop pipelined by call order only: set_input (async, double-buffered, copy stream) +
+            test_model + async D2H of step i+1 are issued before the host waits for step i
   roofline  dominant kernel (by measured device time) vs MEASURED_PEAKS.json, measured live with
-            CUDA events around every C-ABI call of instrumented steps; `kernels` lists all of them
-  cpu_baseline   the reference's own PyTorch-CPU path — its unmodified classifier.Model from the
+            CUDA events around every C-ABI call of instrumented steps; `kernels` lists all of
+            them; `roofline.secondary`: the standalone HBM-bound ops (index_max, query_topk)
+  cpu_baseline   the reference's own PyTorch-CPU path — its unmodified Model class from the
             bytecode build product oracle/_ref/pyref, pool in its own compiled plugin ("kind":
             "reference"; the oracle port only if that cannot be imported) — timed on this box's
-            host cores on a bounded sample (8 clouds of this run's inputs). Its logits are also
+            host cores on a bounded sample (8 clouds of this run's inputs). Its outputs are also
             the parity check of the timed GPU steps ("parity")
   --impl reference   only that CPU arm, same JSON shape with "impl": "reference"
 """
@@ -40,16 +45,37 @@ for p in (ROOT, os.path.join(ROOT, "so-net_b200")):
 
 import torch  # noqa: E402
 
-METRIC = "point-clouds/sec forward (ModelNet40 5000pt, 8x8 SOM)"
 UNIT = "clouds/s"
-B_PER_GPU, NPTS, M_NODES, SOM_K, K_NN, CLASSES = 64, 5000, 64, 9, 3, 40
-WORKLOAD = ("ModelNet40 classifier forward, batch=%d/GPU, N=%d pts, 8x8 SOM, k=%d, som_k=%d, "
-            "fp32, eval (BASELINE.json configs[1])" % (B_PER_GPU, NPTS, K_NN, SOM_K))
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at this workload, from the committed
-# `ncu --set full` captures (profiles/r01_summary.md); None until a capture exists.
+M_NODES, SOM_K, K_NN = 64, 9, 3
+CONFIGS = {
+    "cfg2": dict(task="classifier", B=64, N=5000,
+                 metric="point-clouds/sec forward (ModelNet40 5000pt, 8x8 SOM)",
+                 workload="ModelNet40 classifier forward, batch=64/GPU, N=5000 pts, 8x8 SOM, k=3, "
+                          "som_k=9, fp32, eval (BASELINE.json configs[1])"),
+    "cfg1": dict(task="classifier", B=8, N=1024,
+                 metric="point-clouds/sec forward (ModelNet40 1024pt, 8x8 SOM)",
+                 workload="ModelNet40 classifier forward, batch=8/GPU, N=1024 pts, 8x8 SOM, k=3, "
+                          "som_k=9, fp32, eval (BASELINE.json configs[0])"),
+    "cfg3": dict(task="segmenter", B=32, N=1024,
+                 metric="point-clouds/sec forward + per-point logits (ShapeNetPart 1024pt, 8x8 SOM)",
+                 workload="ShapeNetPart segmenter forward + per-point logits [B,50,N], batch=32/GPU, "
+                          "N=1024 pts, 8x8 SOM, k=3, som_k=9, fp32, eval (BASELINE.json configs[2])"),
+    "cfg4": dict(task="autoencoder", B=32, N=5000,
+                 metric="point-clouds/sec forward + Chamfer (auto-encoder 5000pt, 8x8 SOM)",
+                 workload="Auto-encoder forward (encoder + FC/up-conv decoder, 1280 predicted points) + "
+                          "Chamfer(256 vs 5000) + Chamfer(1280 vs 5000), batch=32/GPU, N=5000 pts, 8x8 "
+                          "SOM, fp32, eval (BASELINE.json configs[3])"),
+}
+METRIC = CONFIGS["cfg2"]["metric"]
+WORKLOAD = CONFIGS["cfg2"]["workload"]
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at the cfg2 workload, from the committed
+# `ncu --set full` captures (profiles/); None until a capture exists.
 NCU_TRAFFIC = {"index_max_f32": 1.4871e9,
                # profiles/r01h_pointresnet_tc_pool_compact.ncu-rep: 33.89 MB read + 2.8 KB written
-               "pointresnet_tc_pool_forward": 33.895e6}
+               "pointresnet_tc_pool_forward": 33.895e6,
+               # profiles/r02d_query_topk.ncu-rep: 3.92 MB read + 198.3 MB written (245.8 MB
+               # algorithmic: part of the mask was still in L2 when the capture ended)
+               "query_topk": 202.26e6}
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -120,40 +146,78 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-# ---- CPU arm: the reference's own PyTorch-CPU path ---------------------------------------------------
-def _cpu_step_fn(sample_B, inp, st_e, st_c):
-    """Returns (step() -> score [sample_B, classes], set_threads(n), kind, pool_desc).
+# ---- task adapters: one table for the GPU arm (sonet_b200) and the CPU arm (the reference) ---------
+def head_name(task):
+    return {"classifier": "classifier", "segmenter": "segmenter", "autoencoder": "decoder"}[task]
 
-    kind "reference": the UNMODIFIED reference — its own models/classifier.py Model (set_input +
-    test_model, exactly the calls of modelnet/train.py:72-76) on its own networks/layers/som
+
+def make_states(task, B, N):
+    """Seeded weights (CPU tensors, reference state_dict keys): encoder seed 1, head seed 2."""
+    from sonet_b200 import networks, synth
+    opt = synth.make_opt(task, batch_size=B, input_pc_num=N)
+    head = {"classifier": networks.Classifier, "segmenter": networks.Segmenter,
+            "autoencoder": networks.Decoder}[task](opt)
+    return (synth.synth_state_dict(networks.Encoder(opt), seed=1),
+            synth.synth_state_dict(head, seed=2))
+
+
+def input_list(task, inp, B, N):
+    """set_input arguments of the task's Model (models/{classifier,segmenter,autoencoder}.py)."""
+    if task == "segmenter":
+        seg = inp.get("seg")
+        if seg is None:
+            seg = inp["seg"] = (torch.arange(B * N, dtype=torch.int64).view(B, N) * 7) % 50
+        return [inp["pc"], inp["sn"], inp["label"], seg, inp["node"], inp["node_knn_I"]]
+    return [inp["pc"], inp["sn"], inp["label"], inp["node"], inp["node_knn_I"]]
+
+
+def result_rows(task, model):
+    """The per-cloud result of a step: what is all-gathered, read back and parity-checked."""
+    if task == "classifier":
+        return model.score                                   # [B, classes]
+    if task == "segmenter":
+        return model.score_segmenter                         # [B, 50, N]
+    return torch.stack((model.chamfer_criteria.forward_loss_array,
+                        model.chamfer_criteria.backward_loss_array), dim=1)   # [B, 2]
+
+
+# ---- CPU arm: the reference's own PyTorch-CPU path ---------------------------------------------------
+def _cpu_step_fn(cfg, sample_B, inp, st_e, st_h):
+    """Returns (step() -> result rows [sample_B, ...], set_threads(n), kind, description).
+
+    kind "reference": the UNMODIFIED reference — its own models/<task>.py Model (set_input +
+    test_model, exactly the calls of modelnet/train.py:72-76) on its own networks/layers/som/losses
     modules, imported from the bytecode build product oracle/_ref/pyref (or /root/reference where
-    that exists) with the three shims of oracle/ref_shims.py; the pool runs in the reference's own
-    compiled plugin (forward_multi_thread_cpu, its faster CPU variant).
+    that exists) with the shims of oracle/ref_shims.py; the pool runs in the reference's own
+    compiled plugin (forward_multi_thread_cpu, its faster CPU variant); Chamfer's Faiss search is
+    the exact brute-force stub (Faiss is not vendored).
     kind "port": the oracle restatement (oracle/oracle.py), only when the reference cannot be
     imported on this machine."""
     from sonet_b200 import synth
-    opt = synth.make_opt("classifier", batch_size=sample_B, input_pc_num=NPTS)
+    task, N = cfg["task"], cfg["N"]
+    opt = synth.make_opt(task, batch_size=sample_B, input_pc_num=N)
+    args = input_list(task, inp, sample_B, N)
     try:
         from oracle import ref_shims
         ref = ref_shims.install(prefer_pyref=True, pool_threads=os.cpu_count() or 1)
         with ref_shims.cpu_only():       # the SOM node buffer follows cuda availability, not opt.device
-            model = ref.classifier.Model(opt)
+            model = getattr(ref, task).Model(opt)
         model.encoder.load_state_dict(st_e)
-        model.classifier.load_state_dict(st_c)
+        getattr(model, head_name(task)).load_state_dict(st_h)
         binary = bool(getattr(ref.index_max, "is_reference_binary", False))
 
         def step():
-            model.set_input(inp["pc"], inp["sn"], inp["label"], inp["node"], inp["node_knn_I"])
+            model.set_input(*args)
             model.test_model()
-            return model.score.detach()
+            return result_rows(task, model).detach()
 
         def set_threads(n):
             torch.set_num_threads(n)
             ref.index_max.pool_threads = n
         where = "oracle/_ref/pyref bytecode" if ref.root != ref_shims.REF else "/root/reference"
         return step, set_threads, "reference", (
-            "reference classifier.Model.set_input/test_model from %s; index_max via %s"
-            % (where, "the reference's compiled forward_multi_thread_cpu" if binary
+            "reference %s.Model.set_input/test_model from %s; index_max via %s"
+            % (task, where, "the reference's compiled forward_multi_thread_cpu" if binary
                else "the C restatement (reference plugin not built)"))
     except Exception as e:                                   # noqa: BLE001
         why = "%s: %s" % (type(e).__name__, e)
@@ -164,7 +228,11 @@ def _cpu_step_fn(sample_B, inp, st_e, st_c):
         with torch.no_grad():
             o = oracle.encoder_forward(st_e, opt, inp["pc"], inp["sn"], inp["node"],
                                        inp["node_knn_I"], fast_pool=threads["n"])
-            return oracle.classifier_forward(st_c, o["feature"])
+            if task == "classifier":
+                return oracle.classifier_forward(st_h, o["feature"])
+            if task == "segmenter":
+                return oracle.segmenter_forward(st_h, opt, o, inp["pc"], inp["sn"], inp["label"])
+            raise RuntimeError("no oracle port of the auto-encoder decoder (%s)" % why)
 
     def set_threads(n):
         torch.set_num_threads(n)
@@ -172,19 +240,18 @@ def _cpu_step_fn(sample_B, inp, st_e, st_c):
     return step, set_threads, "port", "oracle port (reference not importable here: %s)" % why
 
 
-def cpu_arm(steps, warmup, sample_B=8, inp=None):
-    """Time the reference's CPU path on the host cores, on a bounded sample (B=sample_B clouds of
-    the N=5000 workload). Returns the cpu_baseline dict and the scores of the sample."""
+def cpu_arm(cfg, steps, warmup, sample_B=8, inp=None):
+    """Time the reference's CPU path on the host cores, on a bounded sample (sample_B clouds of
+    the config's shape). Returns the cpu_baseline dict and the result rows of the sample."""
     from oracle import build as obuild
     obuild.build_c()
-    from sonet_b200 import networks, synth
+    from sonet_b200 import synth
     cores = os.cpu_count() or 1
-    opt = synth.make_opt("classifier", batch_size=sample_B, input_pc_num=NPTS)
-    st_e = synth.synth_state_dict(networks.Encoder(opt), seed=1)
-    st_c = synth.synth_state_dict(networks.Classifier(opt), seed=2)
+    sample_B = min(sample_B, cfg["B"])
+    st_e, st_h = make_states(cfg["task"], sample_B, cfg["N"])
     if inp is None:
-        inp = synth.synth_inputs(sample_B, NPTS, seed=0)
-    step, set_threads, kind, desc = _cpu_step_fn(sample_B, inp, st_e, st_c)
+        inp = synth.synth_inputs(sample_B, cfg["N"], seed=0)
+    step, set_threads, kind, desc = _cpu_step_fn(cfg, sample_B, inp, st_e, st_h)
 
     # the reference path does not scale to every core count: probe a few thread counts and time
     # the best one (the faster reference number is the one compared against, SURVEY.md §8d)
@@ -201,29 +268,31 @@ def cpu_arm(steps, warmup, sample_B=8, inp=None):
     for _ in range(max(warmup - 1, 0)):
         step()
     times = []
-    score = None
+    rows = None
     for _ in range(steps):
         t0 = time.perf_counter()
-        score = step()
+        rows = step()
         times.append(time.perf_counter() - t0)
     per = sum(times) / len(times)
     return dict(value=sample_B / per, unit=UNIT, cores=best, host_cores=cores,
                 kind=kind, ms_per_step=per * 1e3,
                 thread_probe_s={str(k): round(v, 3) for k, v in probe.items()},
-                sample="%d steps of a B=%d x N=%d classifier forward (%s), best of the probed "
-                       "thread counts, after warm-up" % (steps, sample_B, NPTS, desc)), score
+                sample="%d steps of a B=%d x N=%d %s forward (%s), best of the probed "
+                       "thread counts, after warm-up" % (steps, sample_B, cfg["N"], cfg["task"],
+                                                         desc)), rows
 
 
-def run_reference_arm(args, rank):
+def run_reference_arm(args, rank, cfg):
     if rank != 0:
         return
     steps = max(1, min(args.steps, 5))
     warm = max(1, min(args.warmup, 2))
-    cb, _ = cpu_arm(steps, warm)
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+    cb, _ = cpu_arm(cfg, steps, warm)
+    line = {"impl": "reference", "metric": cfg["metric"], "value": cb["value"], "unit": UNIT,
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "sample_batch": 8},
+            "data": "synthetic", "config": {"workload": cfg["workload"],
+                                            "sample_batch": min(8, cfg["B"])},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
@@ -300,21 +369,83 @@ def kernel_report(profile_steps, peaks):
     return out
 
 
+def standalone_rows(model, cfg, peaks, dev, flush):
+    """HBM-bound API ops that no longer run inside the classifier step (the max is fused into the
+    MLP epilogue, the dense mask is never built): timed standalone on the cfg2 tensors."""
+    from sonet_b200 import ops
+    from sonet_b200 import som as som_mod
+    B, NPTS = 64, 5000
+    g = torch.Generator(device=dev).manual_seed(0)
+    data = torch.randn(B, 384, K_NN * NPTS, device=dev, generator=g)
+    index = torch.randint(0, M_NODES, (B, K_NN * NPTS), device=dev, generator=g, dtype=torch.int32)
+
+    def time_op(fn, reps=5, rounds=4):
+        """CUDA-event time of `reps` back-to-back launches (host launch latency hidden behind
+        the L2 flush write), averaged; working sets exceed L2 so every launch streams HBM."""
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(rounds):
+            flush.zero_()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) / reps)
+        return sum(ts) / len(ts)
+
+    out = []
+    ms_im = time_op(lambda: ops.index_max(data, index, M_NODES, with_values=True))
+    byts = 4.0 * B * 384 * K_NN * NPTS + 4.0 * B * K_NN * NPTS + 8.0 * B * 384 * M_NODES
+    out.append({"kernel": "index_max_f32 (standalone, [64,384,15000] K=64)",
+                "ms": round(ms_im, 4), "bound": "hbm",
+                "achieved": round(byts / (ms_im * 1e-3) / 1e9, 1),
+                "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": round(byts / (ms_im * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                "traffic": NCU_TRAFFIC.get("index_max_f32")})
+    del data, index
+    # SOM kNN with the API-complete outputs of BatchSOM.query_topk (util/som.py:237-269): top-k
+    # assignment + int64 indices + the dense one-hot mask [B,kN,M] int32 (245 MB): HBM-bound
+    from sonet_b200 import synth
+    inp = synth.synth_inputs(B, NPTS, seed=0)
+    pc = inp["pc"].to(dev)
+    bs = som_mod.BatchSOM(8, 8, 3, dev.index or 0, B)
+    bs.node = inp["node"].to(dev)
+    ms_q = time_op(lambda: bs.query_topk(pc, K_NN))
+    kN = K_NN * NPTS
+    byts = B * (12.0 * NPTS + 12.0 * M_NODES + 8.0 * kN + 4.0 * M_NODES + 4.0 * kN * M_NODES)
+    out.append({"kernel": "BatchSOM.query_topk (top-k assignment + dense mask + row_max, one launch), "
+                          "B=64 N=5000",
+                "ms": round(ms_q, 4), "bound": "hbm",
+                "achieved": round(byts / (ms_q * 1e-3) / 1e9, 1),
+                "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": round(byts / (ms_q * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                "traffic": NCU_TRAFFIC.get("query_topk")})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sonet_b200", choices=["sonet_b200", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS),
+                    help="BASELINE.json config (cfg2 = configs[1], the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager op calls instead of CUDA-graph replay")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    cfg = CONFIGS[args.config]
+    task, B, NPTS = cfg["task"], cfg["B"], cfg["N"]
 
     from sonet_b200 import dist as sdist
     rank, local_rank, world = sdist.env_world()
     if args.impl == "reference":
-        run_reference_arm(args, rank)
+        run_reference_arm(args, rank, cfg)
         return
 
     if not torch.cuda.is_available():
@@ -322,25 +453,23 @@ def main():
                          "for the CPU arm")
     rank, local_rank, world = sdist.init_from_env()
     dev = torch.device("cuda", torch.cuda.current_device())
+    import importlib
+
     import torch.distributed as dist
-    from sonet_b200 import _C, classifier, networks, ops, synth
+    from sonet_b200 import _C, ops, synth
     _C.lib()
     peaks = load_peaks()
 
-    B = B_PER_GPU
-    opt = synth.make_opt("classifier", batch_size=B, input_pc_num=NPTS, device=str(dev),
-                         gpu_id=dev.index)
-    cpu_opt = synth.make_opt("classifier", batch_size=B, input_pc_num=NPTS)
-    model = classifier.Model(opt)
-    model.encoder.load_state_dict(synth.synth_state_dict(networks.Encoder(cpu_opt), seed=1))
-    model.classifier.load_state_dict(synth.synth_state_dict(networks.Classifier(cpu_opt), seed=2))
+    opt = synth.make_opt(task, batch_size=B, input_pc_num=NPTS, device=str(dev), gpu_id=dev.index)
+    model = importlib.import_module("sonet_b200." + task).Model(opt)
+    st_e, st_h = make_states(task, B, NPTS)
+    model.encoder.load_state_dict(st_e)
+    getattr(model, head_name(task)).load_state_dict(st_h)
     if not args.no_graph:
         model.enable_cuda_graph(True)                      # one graph launch per step
     inp = synth.synth_inputs(B, NPTS, seed=rank)            # each rank: its own shard
-    keys = ("pc", "sn", "label", "node", "node_knn_I")
-    host = [inp[k].pin_memory() for k in keys]
+    host = [t.pin_memory() for t in input_list(task, inp, B, NPTS)]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)
-    d2h_bytes = B * CLASSES * 4
     total_rows = B * world
 
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
@@ -350,40 +479,70 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    gathered = torch.empty(total_rows, CLASSES, dtype=torch.float32, device=dev) if world > 1 \
-        else None
+    # ---- the step: forward (+ asynchronous all-gather of its result rows) ----------------------------
+    model.set_input(*host)
+    model.test_model()
+    row_shape = tuple(result_rows(task, model).shape[1:])
+    d2h_bytes = B * int(torch.tensor(row_shape).prod()) * 4
+    stage = [torch.empty((B,) + row_shape, dtype=torch.float32, device=dev) for _ in range(2)]
+    gathered = [torch.empty((total_rows,) + row_shape, dtype=torch.float32, device=dev)
+                for _ in range(2)] if world > 1 else None
+    pending = [None, None]
 
-    def gpu_step():
+    def gpu_step(i):
+        """Forward i; its result rows are staged (the graph's static buffer is overwritten by the
+        next replay) and all-gathered ASYNCHRONOUSLY; the gather of step i-1, which ran under this
+        forward, is waited for before the step ends — every gather completes inside a timed step."""
         model.test_model()
-        return sdist.all_gather_rows(model.score, total_rows, out=gathered)
+        rows = result_rows(task, model)
+        if world == 1:
+            return rows
+        stage[i & 1].copy_(rows)
+        pending[i & 1] = dist.all_gather_into_tensor(gathered[i & 1], stage[i & 1], async_op=True)
+        prev = pending[(i - 1) & 1]
+        if prev is not None:
+            prev.wait()
+            pending[(i - 1) & 1] = None
+        return gathered[i & 1]
+
+    def drain():
+        for j in (0, 1):
+            if pending[j] is not None:
+                pending[j].wait()
+                pending[j] = None
 
     # ---- (1) device-resident arm -------------------------------------------------------------------
-    model.set_input(*host)
     torch.cuda.synchronize()
     # rank 0 only: eight nvidia-smi pollers hitting the driver while every timed step contains a
     # cross-rank all-gather turn one rank's stall into everybody's
     sampler = ClockSampler(dev.index)
     if rank == 0:
         sampler.start()                                    # runs through both timed regions
-    for _ in range(args.warmup):
-        gpu_step()
+    for i in range(args.warmup):
+        gpu_step(i)
+    drain()
     time.sleep(0.3)                                        # let nvidia-smi deliver its first sample
-    for _ in range(args.warmup):
-        gpu_step()
+    for i in range(args.warmup):
+        gpu_step(i)
+    drain()
     barrier()
     l0 = ops.KERNEL_LAUNCHES
     evs = []
     wall0 = time.perf_counter()
-    for _ in range(args.steps):
+    out = None
+    for i in range(args.steps):
         flush.zero_()                                      # L2 flush, outside the event pair
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = gpu_step()
+        out = gpu_step(i)
+        if i == args.steps - 1:
+            drain()                                        # the last gather also ends inside a timed step
         e1.record()
         evs.append((e0, e1))
     barrier()
     wall = time.perf_counter() - wall0
-    timed_score = model.score.detach().clone()             # logits of the last timed step
+    timed_rows = result_rows(task, model).detach().clone()  # result of the last timed step
+    timed_gather = out.detach().clone()
     launches = ops.KERNEL_LAUNCHES - l0
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
@@ -393,21 +552,44 @@ def main():
     ms_per_step = total_ms / args.steps
     value = total_rows * args.steps / (total_ms * 1e-3)
 
+    # multi-GPU parity (outside every timed region): the gathered rows of this rank's shard are
+    # bit-identical to what it computed, and rank 0 recomputes rank 1's shard locally (same
+    # seeded inputs and weights): gathered rows == a single-GPU run, bit for bit
+    gather_check = None
+    if world > 1:
+        own_ok = bool(torch.equal(timed_gather[rank * B:(rank + 1) * B], timed_rows))
+        flag = torch.tensor([1 if own_ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        other_ok = None
+        if rank == 0:
+            inp1 = synth.synth_inputs(B, NPTS, seed=1)
+            model.set_input(*input_list(task, inp1, B, NPTS))
+            model.test_model()
+            other_ok = bool(torch.equal(result_rows(task, model), timed_gather[B:2 * B]))
+            model.set_input(*host)
+            model.test_model()
+        gather_check = {"own_shard_bit_identical_all_ranks": bool(flag.item() == 1),
+                        "rank1_shard_recomputed_on_rank0_bit_identical": other_ok}
+        if not gather_check["own_shard_bit_identical_all_ranks"] or other_ok is False:
+            raise SystemExit("bench.py: gathered rows differ from the per-rank results: %s" % gather_check)
+
     # ---- (2) end-to-end arm: host buffers through the public Model API ------------------------------
     # A serving loop over the public API, software-pipelined by call order only: the (async,
-    # double-buffered, copy-stream) set_input of batch i+1 is issued before the logits of batch i
-    # are read back. Every step still copies its full inputs host->device (from pinned memory) and
-    # reads its logits device->host inside the timed region; K steps = K H2D + K D2H.
-    gathered2 = torch.empty_like(gathered) if gathered is not None else None
-
-    pinned_out = [torch.empty(total_rows, CLASSES, dtype=torch.float32).pin_memory() for _ in range(2)]
+    # double-buffered, copy-stream) set_input of batch i+1 is issued before the result of batch i
+    # is read back. Every step still copies its full inputs host->device (from pinned memory) and
+    # reads its result rows device->host inside the timed region; K steps = K H2D + K D2H.
+    pinned_out = [torch.empty((total_rows,) + row_shape, dtype=torch.float32).pin_memory()
+                  for _ in range(2)]
     out_ready = [torch.cuda.Event(), torch.cuda.Event()]
 
     def e2e_run(k_steps):
         def launch(i):                    # H2D + forward (+ all-gather) + async D2H of step i
             model.set_input(*host)
             model.test_model()
-            o = sdist.all_gather_rows(model.score, total_rows, out=(gathered, gathered2)[i & 1])
+            o = result_rows(task, model)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered[i & 1], o.contiguous())
+                o = gathered[i & 1]
             pinned_out[i & 1].copy_(o, non_blocking=True)
             out_ready[i & 1].record()
         launch(0)
@@ -415,7 +597,7 @@ def main():
         for i in range(k_steps):
             if i + 1 < k_steps:
                 launch(i + 1)                              # keep the GPU fed
-            out_ready[i & 1].synchronize()                 # logits of step i are on the host
+            out_ready[i & 1].synchronize()                 # result of step i is on the host
             last = pinned_out[i & 1]
         return last
     e2e_run(args.warmup)
@@ -450,92 +632,46 @@ def main():
     dom = max(modelled, key=lambda r: r["ms"])
     roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"],
                 "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"],
-                "traffic": NCU_TRAFFIC.get(dom["kernel"].split("#")[0]),
+                "traffic": NCU_TRAFFIC.get(dom["kernel"].split("#")[0]) if args.config == "cfg2" else None,
                 "peak_source": peaks["_source"] + (" bf16 burst (kernel timed alone)"
                                                    if dom["bound"] == "tensor"
                                                    else " copy bandwidth"),
                 "ms": dom["ms"], "share_of_step": round(dom["ms"] / kernel_ms, 4),
                 "note": dom.get("note")}
 
-    # the plugin op the reference ships (index_max) no longer runs inside the classifier step (its
-    # max is fused into the MLP epilogue): time it standalone on the cfg-2 tensor for its roofline
-    standalone = []
-    if rank == 0:
-        g = torch.Generator(device=dev).manual_seed(0)
-        data = torch.randn(B, 384, K_NN * NPTS, device=dev, generator=g)
-        index = torch.randint(0, M_NODES, (B, K_NN * NPTS), device=dev, generator=g,
-                              dtype=torch.int32)
-        def time_op(fn, reps=5, rounds=4):
-            """CUDA-event time of `reps` back-to-back launches (host launch latency hidden behind
-            the L2 flush write), averaged; working sets exceed L2 so every launch streams HBM."""
-            for _ in range(3):
-                fn()
-            ts = []
-            for _ in range(rounds):
-                flush.zero_()
-                e0 = torch.cuda.Event(enable_timing=True)
-                e1 = torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(reps):
-                    fn()
-                e1.record()
-                torch.cuda.synchronize()
-                ts.append(e0.elapsed_time(e1) / reps)
-            return ts
-
-        ts = time_op(lambda: ops.index_max(data, index, M_NODES, with_values=True))
-        ms_im = sum(ts) / len(ts)
-        byts = 4.0 * B * 384 * K_NN * NPTS + 4.0 * B * K_NN * NPTS + 8.0 * B * 384 * M_NODES
-        standalone.append({"kernel": "index_max_f32 (standalone, [64,384,15000] K=64)",
-                           "ms": round(ms_im, 4), "bound": "hbm",
-                           "achieved": round(byts / (ms_im * 1e-3) / 1e9, 1),
-                           "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                           "frac": round(byts / (ms_im * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
-                           "traffic": NCU_TRAFFIC.get("index_max_f32")})
-        del data, index
-        # SOM kNN with the API-complete outputs of BatchSOM.query_topk (util/som.py:237-269): top-k
-        # assignment + int64 indices + the dense one-hot mask [B,kN,M] int32 (245 MB): HBM-bound
-        from sonet_b200 import som as som_mod
-        bs = som_mod.BatchSOM(8, 8, 3, dev.index or 0, B)
-        bs.node = model.input_node.detach().clone()
-        ts = time_op(lambda: bs.query_topk(model.pc, K_NN))
-        ms_q = sum(ts) / len(ts)
-        kN = K_NN * NPTS
-        byts = B * (12.0 * NPTS + 12.0 * M_NODES + 8.0 * kN + 4.0 * M_NODES + 4.0 * kN * M_NODES)
-        standalone.append({"kernel": "BatchSOM.query_topk (top-k assignment + dense mask + row_max, one launch), B=64 N=5000",
-                           "ms": round(ms_q, 4), "bound": "hbm",
-                           "achieved": round(byts / (ms_q * 1e-3) / 1e9, 1),
-                           "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                           "frac": round(byts / (ms_q * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
-                           "traffic": None})
+    standalone = standalone_rows(model, cfg, peaks, dev, flush) if rank == 0 else []
 
     # CPU leg (rank 0, N=1): the reference's own CPU path on the first 8 clouds of THIS run's
-    # inputs with THIS run's weights — timed as the cpu_baseline, and its logits double as the
-    # parity check of the logits the timed GPU steps produced (outside every timed region)
+    # inputs with THIS run's weights — timed as the cpu_baseline, and its result rows double as the
+    # parity check of the rows the timed GPU steps produced (outside every timed region)
     cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = {k: inp[k][:8].contiguous() for k in keys}
-        cpu_baseline, ref_score = cpu_arm(steps=3, warmup=1, sample_B=8, inp=sample)
-        got = timed_score[:8].cpu()
-        err = float(((got - ref_score).abs() / ref_score.abs().clamp(min=1.0)).max())
+        sb = min(8, B)
+        sample = {k: v[:sb].contiguous() for k, v in inp.items()}
+        cpu_baseline, ref_rows = cpu_arm(cfg, steps=3, warmup=1, sample_B=sb, inp=sample)
+        got = timed_rows[:sb].cpu()
+        err = float(((got - ref_rows).abs() / ref_rows.abs().clamp(min=1.0)).max())
+        tol = 1e-4
         parity = {"parity_checked": True, "against": cpu_baseline["kind"],
-                  "what": "logits of the timed steps (graph replay) for clouds 0-7 vs the CPU arm's "
-                          "logits on the same inputs/weights",
-                  "max_rel_err": err, "tol": 1e-4, "ok": err <= 1e-4}
+                  "what": "result rows of the timed steps (graph replay) for clouds 0-%d vs the CPU "
+                          "arm's on the same inputs/weights" % (sb - 1),
+                  "max_rel_err": err, "tol": tol, "ok": err <= tol}
         if not parity["ok"]:
-            raise SystemExit("bench.py: GPU logits differ from the CPU reference: %.3e" % err)
+            raise SystemExit("bench.py: GPU results differ from the CPU reference: %.3e" % err)
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+        line = {"metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "global_batch": total_rows,
-                           "parallelism": "dp%d batch-sharded, 1 all-gather of logits/step" % world,
+                "config": {"workload": cfg["workload"], "name": args.config,
+                           "global_batch": total_rows,
+                           "parallelism": "dp%d batch-sharded, 1 async all-gather of the result rows/step"
+                                          % world,
                            "l2": "256 MB flush write between timed steps (outside event pairs)",
                            "weights": "random (seeded), BN stats randomised",
                            "launch": "eager" if args.no_graph else
-                                     "CUDA-graph replay of the step (classifier.Model.enable_cuda_graph)"},
+                                     "CUDA-graph replay of the step (Model.enable_cuda_graph)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes * world},
                 "gpu_launches": launches, "wall_s_timed_region": round(wall, 4),
@@ -546,7 +682,8 @@ def main():
                 "cpu_baseline": cpu_baseline,
                 "parity": parity,
                 "parity_checked": bool(parity and parity["ok"]),
-                "checksum": float(out.double().sum().item())}
+                "gather_check": gather_check,
+                "checksum": float(timed_gather.double().sum().item())}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -179,31 +179,33 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
   return r;
 }
 
-// grid = B: keys (min squared distances) -> sqrt(d + 1e-8) in place, per-cloud means
-__global__ void __launch_bounds__(256)
+// grid = (B, 2): keys (min squared distances) of one direction of one cloud -> sqrt(d + 1e-8) in
+// place and their mean. 1024 threads, fixed order: thread-strided partial sums, xor-shuffle tree
+// inside each warp, then a fixed 32-term tree over the warps.
+constexpr int CC_THREADS = 1024;
+__global__ void __launch_bounds__(CC_THREADS)
     chamfer_cloud_kernel(float* __restrict__ elem_fwd, int Mp, float* __restrict__ elem_bwd, int N,
                          float* __restrict__ fwd_arr, float* __restrict__ bwd_arr) {
-  __shared__ float red[256];
+  __shared__ float wsum[CC_THREADS / 32];
   const int b = blockIdx.x;
+  const bool fwd = blockIdx.y == 0;
+  const int P = fwd ? Mp : N;
+  float* e = (fwd ? elem_fwd : elem_bwd) + static_cast<size_t>(b) * P;
   float s = 0.f;
-  for (int i = threadIdx.x; i < Mp; i += 256) {
-    float* p = elem_fwd + static_cast<size_t>(b) * Mp + i;
-    const float e = __fsqrt_rn(__fadd_rn(*p, 1e-8f));
-    *p = e;
-    s += e;
+  for (int i = threadIdx.x; i < P; i += CC_THREADS) {
+    const float v = __fsqrt_rn(__fadd_rn(e[i], 1e-8f));
+    e[i] = v;
+    s += v;
   }
-  const float f = block_sum_256(s, red);
-  s = 0.f;
-  for (int i = threadIdx.x; i < N; i += 256) {
-    float* p = elem_bwd + static_cast<size_t>(b) * N + i;
-    const float e = __fsqrt_rn(__fadd_rn(*p, 1e-8f));
-    *p = e;
-    s += e;
-  }
-  const float g = block_sum_256(s, red);
-  if (threadIdx.x == 0) {
-    fwd_arr[b] = __fdiv_rn(f, static_cast<float>(Mp));
-    bwd_arr[b] = __fdiv_rn(g, static_cast<float>(N));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = wsum[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) (fwd ? fwd_arr : bwd_arr)[b] = __fdiv_rn(t, static_cast<float>(P));
   }
 }
 
@@ -258,7 +260,7 @@ extern "C" int sonet_chamfer_f32(const float* pred, const float* gt, int B, int 
     rc = check_launch("chamfer(arg-min)");
     if (rc) return rc;
   }
-  chamfer_cloud_kernel<<<B, 256, 0, st>>>(elem_fwd, Mp, elem_bwd, N, loss_fwd_arr, loss_bwd_arr);
+  chamfer_cloud_kernel<<<dim3(B, 2), CC_THREADS, 0, st>>>(elem_fwd, Mp, elem_bwd, N, loss_fwd_arr, loss_bwd_arr);
   chamfer_final_kernel<<<1, 256, 0, st>>>(loss_fwd_arr, loss_bwd_arr, B, loss);
   return check_launch("chamfer");
 }
