@@ -97,6 +97,33 @@ int sonet_som_decenter(const float* x, const float* sn, const float* cluster_mea
                        const int32_t* min_idx_i32, int B, int N, int M, int k,
                        float* centers, float* x_aug, sonet_stream_t stream);
 
+/* ---- f-1: the auto-encoder's up-convolution decoder -------------------------------------------
+ * Replaces UpConv.forward (models/layers.py:214-240; DecoderConv, models/networks.py:394-431):
+ * nearest x2 up-sampling + 3x3 convolution (pad 1) + eval BatchNorm + ReLU, computed as four
+ * parity GEMMs over the LOW-resolution map with K = 4*Cin (the 3x3 taps that coincide after
+ * up-sampling are pre-summed by the host into four [Cout, 4*Cin] matrices, tap-major K).
+ *   sonet_upconv_im2col_f32: in [B,Cin,H,W] -> xcol [4][B][4*Cin][H*W]: group g = py*2+px, tap
+ *     t = a*2+c reads in[b, ci, i + a-1+py, j + c-1+px] (0 outside the map).
+ *   sonet_pointwise_tc_pack_groups: G weight matrices [G,Cout,Cin] -> G consecutive tcgen05 blobs
+ *     (sonet_pointwise_tc_blob_bytes(Cout,Cin) each) with one common pre-scale (*inv_scale).
+ *   sonet_pointwise_tc_grouped_forward: out_g = act(inv_scale * W_g x_g + shift) for G groups in
+ *     ONE launch. x [G*B, C, P]; with scat_w = W > 0 (G must be 4, P = H*W, P_out = 4P) row
+ *     p = i*W + j of group (py,px) is stored at (2i+py)*2W + 2j+px of out [B,Cout,P_out]: the
+ *     parity interleave of the up-convolution; otherwise group g writes out + g*out_gstride.
+ *     splits > 1 divides K (number of 64-channel chunks must be divisible) across CTAs: raw partial
+ *     sums go to scratch [G][splits][B][Cout][P] and a second kernel adds them in a fixed order,
+ *     then shift / ReLU / scatter — for small maps, where one CTA per 128x256 output tile would
+ *     leave most SMs idle while it streams K*256 weights alone. */
+int sonet_upconv_im2col_f32(const float* in, int B, int Cin, int H, int W, float* xcol,
+                            sonet_stream_t stream);
+int sonet_pointwise_tc_pack_groups(const float* W, int G, int Cout, int Cin, void* blob_host,
+                                   float* inv_scale);
+int sonet_pointwise_tc_grouped_forward(const float* x, int C, int B, int P, const void* blob,
+                                       long long blob_gstride, float inv_scale, const float* shift,
+                                       int Cout, int relu, int groups, int splits, int scat_w,
+                                       int P_out, long long out_gstride, float* out, float* scratch,
+                                       sonet_stream_t stream);
+
 /* ---- f-4: batch-SOM training --------------------------------------------------------------------
  * Replaces BatchSOM.batch_update / BatchSOM.optimize (util/som.py:295-366): T iterations of
  * {nearest-node assignment, per-node mean, neighbourhood-weighted node update} per cloud, in ONE

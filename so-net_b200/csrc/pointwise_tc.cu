@@ -65,7 +65,33 @@ struct Dims {
   int vec4;      // 16-byte activation fetch is legal (P % 4 == 0, 16-byte aligned bases)
   int tma;       // activation chunks by tensor-map TMA (single source, P % 64 == 0)
   float inv;     // 1 / weight pre-scale
+  // ---- grouped / split-K / scatter extensions (the up-convolution decoder, csrc/upconv.cu) ----
+  int groups;    // independent GEMMs sharing shapes: x is [groups*B, C, P], one weight blob each
+  int splits;    // K split: an item covers kchunks/splits chunks and writes a raw partial sum
+  int kpi;       // k chunks per item (= kchunks / splits)
+  int row_tiles; // 128-row tiles per group
+  int scat_w;    // > 0: group g = (py, px) parity of a x2 up-convolution over a [*, scat_w] map;
+                 //      row p = i*W + j is stored at (2i+py)*2W + 2j+px of a [B, Cout, P_out] map
+  int P_out;     // point stride of `out` (= P unless scattering)
+  long long blob_gstride;   // bytes between the weight blobs of consecutive groups
+  long long out_gstride;    // floats between the outputs of consecutive groups (0 when scattering)
+  long long out_sstride;    // floats between the partial sums of consecutive K splits
 };
+struct Item {
+  int g, tile, nt, kc0;
+};
+__device__ __forceinline__ Item decode_item(const Dims& d, int item) {
+  // n-tile fastest: the activation tile stays hot in L2; then K split, row tile, group
+  Item r;
+  r.nt = item % d.ntiles;
+  int t = item / d.ntiles;
+  const int sp = t % d.splits;
+  t /= d.splits;
+  r.tile = t % d.row_tiles;
+  r.g = t / d.row_tiles;
+  r.kc0 = sp * d.kpi;
+  return r;
+}
 __host__ __device__ inline int ntile_width(int Cout, int nt) {
   const int cpad = (Cout + 63) / 64 * 64;
   return min(NT, cpad - nt * NT);
@@ -103,9 +129,8 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
   // warp index through a shuffle: ptxas then knows the role branches are warp-uniform
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const long long rows = static_cast<long long>(d.B) * d.P;
-  const int row_tiles = static_cast<int>((rows + TILE - 1) / TILE);
-  const int items = row_tiles * d.ntiles;   // n-tile fastest: the activation tile stays hot in L2
+  const long long rows = static_cast<long long>(d.B) * d.P;   // rows of ONE group
+  const int items = d.groups * d.row_tiles * d.splits * d.ntiles;
   const int my_items =
       (static_cast<int>(blockIdx.x) < items) ? (items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int Cin = d.C0 + d.C1;
@@ -141,13 +166,14 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
     if (lane == 0) {
       uint32_t q = 0;
       for (int it = 0; it < my_items; ++it) {
-        const int item = blockIdx.x + it * gridDim.x;
-        const int nt = item % d.ntiles;
+        const Item im = decode_item(d, blockIdx.x + it * gridDim.x);
+        const int nt = im.nt;
         const int nw = ntile_width(d.Cout, nt);
         // blob: n-tile nt starts after nt full-width tiles; a 64-k chunk = two [nw x 32] stages
-        const size_t off0 = static_cast<size_t>(nt) * d.kchunks * W_BYTES;
+        const size_t off0 = static_cast<size_t>(im.g) * d.blob_gstride +
+                            static_cast<size_t>(nt) * d.kchunks * W_BYTES;
         const uint32_t bytes = static_cast<uint32_t>(nw) * WK * 4;
-        for (int kc = 0; kc < d.kchunks; ++kc) {
+        for (int kc = im.kc0; kc < im.kc0 + d.kpi; ++kc) {
           const int halves = (d.cin_pad - kc * KCH > WK) ? 2 : 1;   // the MMA warp agrees
           for (int hh = 0; hh < halves; ++hh, ++q) {
             const uint32_t slot = q % NSTAGE_W, use = q / NSTAGE_W;
@@ -155,7 +181,7 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
             mbar_arrive_expect_tx(&full_w[slot], bytes);
             bulk_g2s(smem + OFF_W + slot * WS_BYTES,
                      blob + off0 + (static_cast<size_t>(kc) * 2 + hh) * bytes, bytes, &full_w[slot]);
-            if (it == 0 && hh == 0) PW_TL(0, kc);
+            if (it == 0 && hh == 0) PW_TL(0, kc - im.kc0);
           }
         }
       }
@@ -167,8 +193,8 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
                      w_base = static_cast<uint32_t>(__cvta_generic_to_shared(smem + OFF_W));
       uint32_t qa = 0, qw = 0;
       for (int it = 0; it < my_items; ++it) {
-        const int item = blockIdx.x + it * gridDim.x;
-        const int nt = item % d.ntiles;
+        const Item im = decode_item(d, blockIdx.x + it * gridDim.x);
+        const int nt = im.nt;
         const int nw = ntile_width(d.Cout, nt);
         const uint32_t idesc = tc::idesc_f16_f32(TILE, nw);
         const int buf = it & 1;
@@ -176,10 +202,10 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
         if (use > 0) tc::mbar_wait_bounded(&d_empty[buf], (use - 1) & 1, 201);
         tc::fence_after_sync();
         const uint32_t dcol = tm + buf * NT;
-        for (int kc = 0; kc < d.kchunks; ++kc, ++qa) {
+        for (int kc = im.kc0; kc < im.kc0 + d.kpi; ++kc, ++qa) {
           const uint32_t sa = qa % NSTAGE, pa = (qa / NSTAGE) & 1;
           tc::mbar_wait_bounded(&full_a[sa], pa, 203);
-          if (it == 0) PW_TL(1, 3 * kc + 1);
+          if (it == 0) PW_TL(1, 3 * (kc - im.kc0) + 1);
           const uint32_t as = a_base + sa * A_BYTES;
           const int nks = min(4, (d.cin_pad - kc * KCH) / 16);
           const int halves = (nks > 2) ? 2 : 1;
@@ -187,7 +213,7 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
             const uint32_t sw = qw % NSTAGE_W, pw = (qw / NSTAGE_W) & 1;
             tc::mbar_wait_bounded(&full_w[sw], pw, 202);
             tc::fence_after_sync();
-            if (it == 0 && hh == 0) PW_TL(1, 3 * kc);
+            if (it == 0 && hh == 0) PW_TL(1, 3 * (kc - im.kc0));
             const uint32_t ws = w_base + sw * WS_BYTES;
             // A: [128 x 64] image, SBO 1024, this half starts 2 k-steps (512 B) in;
             // B: [nw x 32] image, SBO 512
@@ -195,14 +221,14 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
                            al = tc::smem_desc(as + A_BYTES / 2 + hh * 512, 128, 1024),
                            bh = tc::smem_desc(ws, 128, 512),
                            bl = tc::smem_desc(ws + nw * WK * 2, 128, 512);
-            const uint32_t acc = (kc | hh) != 0;
+            const uint32_t acc = ((kc - im.kc0) | hh) != 0;
             const int nk = (hh == 0) ? min(nks, 2) : nks - 2;
             if (nk == 2) tc::mma_ss_stage<2>(dcol, ah, al, bh, bl, idesc, acc);
             else tc::mma_ss_stage<1>(dcol, ah, al, bh, bl, idesc, acc);
             tc::commit_elect(&empty_w[sw]);
           }
           tc::commit_elect(&empty_a[sa]);
-          if (it == 0) PW_TL(1, 3 * kc + 2);
+          if (it == 0) PW_TL(1, 3 * (kc - im.kc0) + 2);
         }
         tc::commit_elect(&d_full[buf]);
       }
@@ -216,13 +242,15 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
     // (Register-staged loads were bytes-in-flight bound: 4-5k cycles per chunk in the timeline.)
     // Each thread converts row m's 32 channels, which other threads copied: wait_group + a named
     // barrier before the read, another one before the tile is refilled with the next chunk.
-    const uint32_t total = static_cast<uint32_t>(my_items) * d.kchunks;
+    const uint32_t total = static_cast<uint32_t>(my_items) * d.kpi;
     float* stg = reinterpret_cast<float*>(smem + OFF_STG) + (half * 32) * TILE + m;
     const uint32_t stg_s = smem_u32(stg);
     auto issue = [&](uint32_t qq) {
-      const int it = qq / d.kchunks, kc = qq - it * d.kchunks;
-      const int item = blockIdx.x + it * gridDim.x;
-      const long long R0 = static_cast<long long>(item / d.ntiles) * TILE;
+      const int it = qq / d.kpi;
+      const Item im = decode_item(d, blockIdx.x + it * gridDim.x);
+      const int kc = im.kc0 + (qq - it * d.kpi);
+      const long long R0 = static_cast<long long>(im.tile) * TILE;
+      const int gb = im.g * d.B;                 // first cloud of this group in x [groups*B, C, P]
       if (d.tma) {
         // two [64 p][64 c] boxes; staging layout [box][c][64 p]. Rows past the last cloud give
         // b >= B (fully out of range): the box is zero-filled and still counts its bytes.
@@ -233,8 +261,10 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             const long long R = R0 + 64 * i;
-            const int b = static_cast<int>(R / d.P);
-            const int p = static_cast<int>(R - static_cast<long long>(b) * d.P);
+            const int bl = static_cast<int>(R / d.P);
+            const int p = static_cast<int>(R - static_cast<long long>(bl) * d.P);
+            // rows past the group's last cloud must not read the next group: push them out of range
+            const int b = (bl < d.B) ? gb + bl : d.groups * d.B;
             asm volatile(
                 "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
                 "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(sdst + i * (STG_BYTES / 2)),
@@ -250,8 +280,9 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
         // across a cloud boundary because P % 4 == 0)
         const long long R = R0 + 4 * lane;
         const bool valid = R < rows;
-        const int b = valid ? static_cast<int>(R / d.P) : 0;
-        const int p = valid ? static_cast<int>(R - static_cast<long long>(b) * d.P) : 0;
+        const int bl = valid ? static_cast<int>(R / d.P) : 0;
+        const int p = valid ? static_cast<int>(R - static_cast<long long>(bl) * d.P) : 0;
+        const int b = gb + bl;
         const float* r0 = x0 + static_cast<size_t>(b) * d.C0 * d.P + p;
         const float* r1 = d.C1 ? x1 + static_cast<size_t>(b) * d.C1 * d.P + p : x0;
         const int w8 = (t >> 5);
@@ -271,8 +302,9 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
       } else {
         const long long R = R0 + m;
         const bool valid = R < rows;
-        const int b = valid ? static_cast<int>(R / d.P) : 0;
-        const int p = valid ? static_cast<int>(R - static_cast<long long>(b) * d.P) : 0;
+        const int bl = valid ? static_cast<int>(R / d.P) : 0;
+        const int p = valid ? static_cast<int>(R - static_cast<long long>(bl) * d.P) : 0;
+        const int b = gb + bl;
         const float* r0 = x0 + static_cast<size_t>(b) * d.C0 * d.P + p;
         const float* r1 = d.C1 ? x1 + static_cast<size_t>(b) * d.C1 * d.P + p : x0;
         const int c_base = kc * KCH + half * 32;
@@ -351,20 +383,28 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
     const uint32_t lane_base = tm + (static_cast<uint32_t>(q4 * 32) << 16);
     const float floor_v = d.relu ? 0.f : -__int_as_float(0x7f800000);   // ReLU as one max
     for (int it = 0; it < my_items; ++it) {
-      const int item = blockIdx.x + it * gridDim.x;
-      const int nt = item % d.ntiles;
+      const Item im = decode_item(d, blockIdx.x + it * gridDim.x);
+      const int nt = im.nt;
       const int nw = ntile_width(d.Cout, nt);
-      const long long R = static_cast<long long>(item / d.ntiles) * TILE + m;
+      const long long R = static_cast<long long>(im.tile) * TILE + m;
       const bool valid = R < rows;
       const int b = valid ? static_cast<int>(R / d.P) : 0;
       const int p = valid ? static_cast<int>(R - static_cast<long long>(b) * d.P) : 0;
+      // where row (b, p) of this group / K split lands in `out`
+      size_t obase = static_cast<size_t>(im.g) * d.out_gstride +
+                     static_cast<size_t>(im.kc0 / d.kpi) * d.out_sstride;
+      int po = p;
+      if (d.scat_w > 0) {   // x2 up-convolution: parity (py, px) = group
+        const int i = p / d.scat_w, j = p - i * d.scat_w;
+        po = (2 * i + (im.g >> 1)) * 2 * d.scat_w + 2 * j + (im.g & 1);
+      }
       const int buf = it & 1;
       tc::mbar_wait_bounded(&d_full[buf], (it >> 1) & 1, 205);
       tc::fence_after_sync();
       if (warp == 4 && it < 4) PW_TL(3, 2 * it);
       const float* arow = nullptr;
       if (addend != nullptr && valid) {
-        const int g = min(max(__ldg(gidx + R), 0), d.G - 1);
+        const int g = min(max(__ldg(gidx + static_cast<long long>(im.g) * rows + R), 0), d.G - 1);
         arow = addend + static_cast<size_t>(b) * d.Cout * d.G + g;
       }
       const int cw = nw >> 1;                      // columns per warpgroup (multiple of 32)
@@ -402,7 +442,7 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
           if (lane == 0) mbar_arrive(&d_empty[buf]);
         }
         if (valid) {
-          float* o = out + (static_cast<size_t>(b) * d.Cout + cg) * d.P + p;
+          float* o = out + obase + (static_cast<size_t>(b) * d.Cout + cg) * d.P_out + po;
           // 16 columns at a time: the gathered addends (one per output element, segmenter layer 1)
           // are all loaded before the first dependent add, like the shift values above
           auto emit16 = [&](const uint32_t (&v)[16], int i0) {
@@ -416,7 +456,7 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
             for (int i = 0; i < 16; ++i) {
               if (all_real || cg + i0 + i < d.Cout) {
                 const float y = fmaf(__uint_as_float(v[i]), d.inv, sh[i0 + i]) + ad[i];
-                o[static_cast<size_t>(i0 + i) * d.P] = fmaxf(y, floor_v);
+                o[static_cast<size_t>(i0 + i) * d.P_out] = fmaxf(y, floor_v);
               }
             }
           };
@@ -444,23 +484,22 @@ extern "C" long long sonet_pointwise_tc_blob_bytes(int Cout, int Cin) {
   return static_cast<long long>(cpad) * kch * KCH * 4;
 }
 
-extern "C" int sonet_pointwise_tc_pack(const float* W, int Cout, int Cin, void* blob_host,
-                                       float* inv_scale) {
-  using namespace sonet;
-  using namespace sonet::pwt;
-  SONET_REQUIRE(W && blob_host && inv_scale && Cout >= 1 && Cin >= 1, "pointwise_tc_pack: bad args");
-  const long long bytes = sonet_pointwise_tc_blob_bytes(Cout, Cin);
-  unsigned char* blob = static_cast<unsigned char*>(blob_host);
-  std::memset(blob, 0, static_cast<size_t>(bytes));
+static float tc_weight_scale(const float* W, size_t n) {
   float mx = 0.f;
-  for (size_t i = 0, n = static_cast<size_t>(Cout) * Cin; i < n; ++i) mx = std::max(mx, std::fabs(W[i]));
+  for (size_t i = 0; i < n; ++i) mx = std::max(mx, std::fabs(W[i]));
   float scale = 1.f;
   if (mx > 0.f && std::isfinite(mx)) {
     int e;
     std::frexp(mx, &e);
     scale = std::ldexp(1.f, 9 - e);   // max|scale*W| in [256, 512)
   }
-  *inv_scale = 1.f / scale;
+  return scale;
+}
+
+static void tc_pack_matrix(const float* W, int Cout, int Cin, unsigned char* blob, float scale) {
+  using namespace sonet::pwt;
+  const long long bytes = sonet_pointwise_tc_blob_bytes(Cout, Cin);
+  std::memset(blob, 0, static_cast<size_t>(bytes));
   const int cpad = (Cout + 63) / 64 * 64;
   const int kch = ((Cin + 15) / 16 * 16 + KCH - 1) / KCH;
   const int ntiles = (cpad + NT - 1) / NT;
@@ -489,6 +528,31 @@ extern "C" int sonet_pointwise_tc_pack(const float* W, int Cout, int Cin, void* 
       }
     }
   }
+}
+
+extern "C" int sonet_pointwise_tc_pack(const float* W, int Cout, int Cin, void* blob_host,
+                                       float* inv_scale) {
+  using namespace sonet;
+  SONET_REQUIRE(W && blob_host && inv_scale && Cout >= 1 && Cin >= 1, "pointwise_tc_pack: bad args");
+  const float scale = tc_weight_scale(W, static_cast<size_t>(Cout) * Cin);
+  *inv_scale = 1.f / scale;
+  tc_pack_matrix(W, Cout, Cin, static_cast<unsigned char*>(blob_host), scale);
+  return SONET_OK;
+}
+
+// G matrices [G, Cout, Cin] packed back to back (sonet_pointwise_tc_blob_bytes each) with ONE
+// common power-of-two pre-scale: the weight blobs of a grouped launch.
+extern "C" int sonet_pointwise_tc_pack_groups(const float* W, int G, int Cout, int Cin,
+                                              void* blob_host, float* inv_scale) {
+  using namespace sonet;
+  SONET_REQUIRE(W && blob_host && inv_scale && G >= 1 && Cout >= 1 && Cin >= 1,
+                "pointwise_tc_pack_groups: bad args");
+  const size_t per = static_cast<size_t>(Cout) * Cin;
+  const float scale = tc_weight_scale(W, per * G);
+  *inv_scale = 1.f / scale;
+  const long long bytes = sonet_pointwise_tc_blob_bytes(Cout, Cin);
+  for (int g = 0; g < G; ++g)
+    tc_pack_matrix(W + g * per, Cout, Cin, static_cast<unsigned char*>(blob_host) + g * bytes, scale);
   return SONET_OK;
 }
 
@@ -523,11 +587,17 @@ static bool make_activation_map(CUtensorMap* m, const float* x, int B, int C, in
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+struct TcExt {   // grouped / split-K / scatter launch options (defaults = the plain layer)
+  int groups = 1, splits = 1, scat_w = 0, P_out = 0;
+  long long blob_gstride = 0, out_gstride = 0, out_sstride = 0;
+};
+
 static int launch_pointwise_tc(const float* x0, int C0, const float* x1, int C1, int B,
                                           int P, const void* blob, float inv_scale,
                                           const float* shift, int Cout, int relu,
                                           const float* addend, const int32_t* gidx, int G,
-                                          float* out, long long* dbg, sonet_stream_t stream) {
+                                          float* out, long long* dbg, sonet_stream_t stream,
+                                          const TcExt& ext = TcExt()) {
   using namespace sonet;
   using namespace sonet::pwt;
   SONET_REQUIRE(B >= 0 && P >= 0 && C0 >= 1 && C1 >= 0 && Cout >= 1, "pointwise_tc: bad dimension");
@@ -549,9 +619,20 @@ static int launch_pointwise_tc(const float* x0, int C0, const float* x1, int C1,
     const char* e = getenv("SONET_PW_TMA");
     return e != nullptr && e[0] == '0';
   }();
-  d.tma = (!tma_off && C1 == 0 && make_activation_map(&xmap, x0, B, C0, P)) ? 1 : 0;
+  SONET_REQUIRE(ext.groups >= 1 && ext.splits >= 1 && d.kchunks % ext.splits == 0,
+                "pointwise_tc: %d K chunks cannot be split %d ways", d.kchunks, ext.splits);
+  d.groups = ext.groups;
+  d.splits = ext.splits;
+  d.kpi = d.kchunks / ext.splits;
+  d.scat_w = ext.scat_w;
+  d.P_out = ext.P_out > 0 ? ext.P_out : P;
+  d.blob_gstride = ext.blob_gstride;
+  d.out_gstride = ext.out_gstride;
+  d.out_sstride = ext.out_sstride;
+  d.tma = (!tma_off && C1 == 0 && make_activation_map(&xmap, x0, ext.groups * B, C0, P)) ? 1 : 0;
   const long long rows = static_cast<long long>(B) * P;
-  const long long items = (rows + TILE - 1) / TILE * d.ntiles;
+  d.row_tiles = static_cast<int>((rows + TILE - 1) / TILE);
+  const long long items = static_cast<long long>(d.row_tiles) * d.ntiles * ext.groups * ext.splits;
   SONET_REQUIRE(items < (1LL << 31), "pointwise_tc: too many tiles");
   SONET_REQUIRE(SMEM_BYTES <= max_smem_optin(), "pointwise_tc: needs %d B of shared memory", SMEM_BYTES);
   cudaFuncSetAttribute(pointwise_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -568,6 +649,74 @@ extern "C" int sonet_pointwise_tc_forward(const float* x0, int C0, const float* 
                                           float* out, sonet_stream_t stream) {
   return launch_pointwise_tc(x0, C0, x1, C1, B, P, blob, inv_scale, shift, Cout, relu, addend, gidx, G,
                              out, nullptr, stream);
+}
+
+namespace sonet {
+// partial [G][S][B][Cout][P] (raw K-split sums) -> out: sum over S in ascending order (fixed ->
+// deterministic), + shift, ReLU, and the up-convolution parity scatter.
+__global__ void __launch_bounds__(256)
+    splitk_reduce_kernel(const float* __restrict__ part, int G, int S, int B, int Cout, int P,
+                         const float* __restrict__ shift, int relu, int scat_w, int P_out,
+                         long long out_gstride, float* __restrict__ out) {
+  const long long per_split = static_cast<long long>(B) * Cout * P;
+  const long long total = per_split * G;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(t / per_split);
+    const long long r = t - g * per_split;
+    const int p = static_cast<int>(r % P);
+    const long long bc = r / P;                    // b * Cout + co
+    const int co = static_cast<int>(bc % Cout);
+    const float* src = part + static_cast<long long>(g) * S * per_split + r;
+    float acc = src[0];
+    for (int s = 1; s < S; ++s) acc += src[s * per_split];
+    if (shift != nullptr) acc += __ldg(shift + co);
+    if (relu) acc = fmaxf(acc, 0.f);
+    int po = p;
+    if (scat_w > 0) {
+      const int i = p / scat_w, j = p - i * scat_w;
+      po = (2 * i + (g >> 1)) * 2 * scat_w + 2 * j + (g & 1);
+    }
+    out[static_cast<long long>(g) * out_gstride + bc * P_out + po] = acc;
+  }
+}
+}  // namespace sonet
+
+extern "C" int sonet_pointwise_tc_grouped_forward(const float* x, int C, int B, int P,
+                                                  const void* blob, long long blob_gstride,
+                                                  float inv_scale, const float* shift, int Cout,
+                                                  int relu, int groups, int splits, int scat_w,
+                                                  int P_out, long long out_gstride, float* out,
+                                                  float* scratch, sonet_stream_t stream) {
+  using namespace sonet;
+  SONET_REQUIRE(groups >= 1 && splits >= 1 && scat_w >= 0, "pointwise_tc_grouped: bad group/split");
+  SONET_REQUIRE(scat_w == 0 || (groups == 4 && P % scat_w == 0 && P_out == 4 * P && out_gstride == 0),
+                "pointwise_tc_grouped: the x2 scatter needs 4 parity groups, P = H*W, P_out = 4P");
+  SONET_REQUIRE(splits == 1 || scratch != nullptr, "pointwise_tc_grouped: split-K needs scratch");
+  if (B == 0 || P == 0) return SONET_OK;
+  if (P_out <= 0) P_out = P;
+  TcExt e;
+  e.groups = groups;
+  e.splits = splits;
+  e.blob_gstride = blob_gstride;
+  if (splits == 1) {
+    e.scat_w = scat_w;
+    e.P_out = P_out;
+    e.out_gstride = out_gstride;
+    return launch_pointwise_tc(x, C, nullptr, 0, B, P, blob, inv_scale, shift, Cout, relu, nullptr,
+                               nullptr, 0, out, nullptr, stream, e);
+  }
+  const long long per_split = static_cast<long long>(B) * Cout * P;
+  e.out_sstride = per_split;
+  e.out_gstride = per_split * splits;
+  int rc = launch_pointwise_tc(x, C, nullptr, 0, B, P, blob, inv_scale, nullptr, Cout, 0, nullptr,
+                               nullptr, 0, scratch, nullptr, stream, e);
+  if (rc) return rc;
+  const long long total = per_split * groups;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * sm_count()));
+  splitk_reduce_kernel<<<grid, 256, 0, as_stream(stream)>>>(scratch, groups, splits, B, Cout, P, shift,
+                                                            relu, scat_w, P_out, out_gstride, out);
+  return check_launch("splitk_reduce");
 }
 
 extern "C" int sonet_debug_pointwise_tc_timeline(const float* x0, int C0, int B, int P,

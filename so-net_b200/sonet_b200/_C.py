@@ -25,6 +25,12 @@ _SIGNATURES = {
     "sonet_som_query_topk": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p],
     "sonet_som_mask": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sonet_upconv_im2col_f32": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sonet_pointwise_tc_pack_groups": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sonet_pointwise_tc_grouped_forward": [c_void_p, c_int, c_int, c_int, c_void_p,
+                                           ctypes.c_longlong, ctypes.c_float, c_void_p, c_int, c_int,
+                                           c_int, c_int, c_int, c_int, ctypes.c_longlong, c_void_p,
+                                           c_void_p, c_void_p],
     "sonet_som_train": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                         c_void_p, c_void_p, c_void_p],
     "sonet_augment_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -278,9 +278,20 @@ class MyConv2d(_PointwiseConvBase):
         return x
 
 
+def _pick_splits(kchunks, base_items, target=120, cap=32):
+    """K split of a grouped tcgen05 launch: the smallest power of two dividing the number of
+    64-channel K chunks that brings the item count to ~one wave of SMs."""
+    s = 1
+    while s * 2 <= cap and kchunks % (s * 2) == 0 and base_items * s < target:
+        s *= 2
+    return s
+
+
 class UpConv(nn.Module):
-    """Nearest x2 upsample + 3x3 conv (models/layers.py:214-240); decoder only — PyTorch/cuDNN
-    (out of the hot-path scope)."""
+    """Nearest x2 upsample + 3x3 conv + BN + act (models/layers.py:214-240), the decoder's
+    building block. Eval fast path: four parity GEMMs over the LOW-resolution
+    map on tcgen05 (csrc/upconv.cu, csrc/pointwise_tc.cu) — the up-sampled image is never built
+    and the 3x3 taps that coincide after up-sampling are pre-summed (K = 4*Cin, not 9*Cin)."""
 
     def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=0,
                  output_padding=0, bias=True, activation=None, normalization=None):
@@ -290,6 +301,9 @@ class UpConv(nn.Module):
         self.up_sample = nn.Upsample(scale_factor=2)
         self.conv = MyConv2d(in_channels, out_channels, kernel_size=3, stride=1, padding=1,
                              bias=True, activation=activation, normalization=normalization)
+        self._tc_key = None
+        self._tc_pack = None
+        self._scratch = {}
         self.weight_init()
 
     def weight_init(self):
@@ -299,8 +313,89 @@ class UpConv(nn.Module):
         if c.bias is not None:
             nn.init.constant_(c.bias, 0.001)
 
+    # ---- eval fast path --------------------------------------------------------------------------
+    def _fast(self, x):
+        c = self.conv.conv
+        return (_fast_ok(self, x) and x.dim() == 4 and c.kernel_size == (3, 3)
+                and c.stride == (1, 1) and c.padding == (1, 1) and c.dilation == (1, 1)
+                and c.groups == 1 and c.out_channels >= 64 and c.in_channels >= 16
+                and self.normalization in (None, 'batch') and self.activation in (None, 'relu')
+                and os.environ.get("SONET_TC", "1") != "0")
+
+    def _packed(self):
+        """BN-folded, parity-combined weights as tcgen05 blobs; re-packed when a source tensor
+        changes. Wg[g=(py,px)][co][(a,c)*Cin + ci] = sum of the 3x3 taps (dy,dx) that read low-res
+        neighbour (a,c) for output parity (py,px): rows {0}|{1,2} (py=0) or {0,1}|{2} (py=1)."""
+        c = self.conv.conv
+        norm = self.conv.norm if self.normalization == 'batch' else None
+        srcs = [c.weight, c.bias]
+        if norm is not None:
+            srcs += [norm.weight, norm.bias, norm.running_mean, norm.running_var]
+        key = tuple((t.data_ptr(), t._version, t.device) for t in srcs if t is not None)
+        if key != self._tc_key:
+            with torch.no_grad():
+                w = c.weight.detach().float()                              # [Cout,Cin,3,3]
+                shift = c.bias.detach().float() if c.bias is not None else \
+                    torch.zeros(w.shape[0], device=w.device)
+                if norm is not None:
+                    sc = norm.weight.detach() / torch.sqrt(norm.running_var.detach() + norm.eps)
+                    shift = (shift - norm.running_mean.detach()) * sc + norm.bias.detach()
+                    w = w * sc[:, None, None, None]
+                sets = (((0,), (1, 2)), ((0, 1), (2,)))                    # [parity][tap] -> kernel rows
+                Cout, Cin = w.shape[0], w.shape[1]
+                Wg = torch.zeros(4, Cout, 4, Cin, device=w.device)
+                for py in range(2):
+                    for px in range(2):
+                        for a in range(2):
+                            for cc in range(2):
+                                acc = 0
+                                for dy in sets[py][a]:
+                                    for dx in sets[px][cc]:
+                                        acc = acc + w[:, :, dy, dx]
+                                Wg[py * 2 + px, :, a * 2 + cc, :] = acc
+                blob4, per4, inv4 = ops.pointwise_tc_pack_groups(Wg.view(4, Cout, 4 * Cin))
+                # 1x1 input: only the tap that lands on the single pixel survives -> one dense
+                # layer Cin -> 4*Cout (output channel co*4 + py*2 + px)
+                W1 = torch.stack([Wg[g, :, (1 - (g >> 1)) * 2 + (1 - (g & 1)), :] for g in range(4)],
+                                 dim=1).reshape(1, Cout * 4, Cin)
+                blob1, per1, inv1 = ops.pointwise_tc_pack_groups(W1)
+                dev = w.device
+                self._tc_pack = dict(blob4=blob4.to(dev), per4=per4, inv4=inv4, blob1=blob1.to(dev),
+                                     per1=per1, inv1=inv1, shift=shift.contiguous(),
+                                     shift1=shift.repeat_interleave(4).contiguous())
+            self._tc_key = key
+        return self._tc_pack
+
+    def _scratch_for(self, n, dev):
+        buf = self._scratch.get(dev)
+        if buf is None or buf.numel() < n:
+            buf = self._scratch[dev] = torch.empty(n, dtype=torch.float32, device=dev)
+        return buf
+
     def forward(self, x):
-        return self.conv(self.up_sample(x))
+        if not self._fast(x):
+            return self.conv(self.up_sample(x))
+        pk = self._packed()
+        B, Cin, H, W = x.shape
+        Cout = self.conv.conv.out_channels
+        relu = self.activation == 'relu'
+        x = x.contiguous()
+        if H == 1 and W == 1:
+            kch = (Cin + 63) // 64
+            splits = _pick_splits(kch, ((B + 127) // 128) * ((4 * Cout + 255) // 256))
+            scratch = self._scratch_for(splits * B * 4 * Cout, x.device) if splits > 1 else None
+            y = ops.pointwise_tc_grouped(x.view(B, Cin, 1), pk["blob1"], pk["per1"], pk["inv1"],
+                                         pk["shift1"], 4 * Cout, relu, groups=1, splits=splits,
+                                         scratch=scratch)
+            return y.view(B, Cout, 2, 2)
+        xcol = ops.upconv_im2col(x)                                       # [4B, 4Cin, HW]
+        P = H * W
+        kch = (4 * Cin + 63) // 64
+        splits = _pick_splits(kch, 4 * ((B * P + 127) // 128) * ((Cout + 255) // 256))
+        scratch = self._scratch_for(4 * splits * B * Cout * P, x.device) if splits > 1 else None
+        y = ops.pointwise_tc_grouped(xcol, pk["blob4"], pk["per4"], pk["inv4"], pk["shift"], Cout,
+                                     relu, groups=4, splits=splits, scat_w=W, scratch=scratch)
+        return y.view(B, Cout, 2 * H, 2 * W)
 
 
 class EquivariantLayer(_PointwiseConvBase):

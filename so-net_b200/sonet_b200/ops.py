@@ -361,6 +361,62 @@ def pointwise_tc_pack(W):
     return blob, float(inv.value)
 
 
+def pointwise_tc_pack_groups(Wg):
+    """Wg [G,Cout,Cin] folded fp32 (any device) -> (blob uint8 CPU tensor of G consecutive blobs,
+    bytes per blob, common inv_scale)."""
+    import ctypes
+    lib = _C.lib()
+    Wc = Wg.detach().to("cpu", torch.float32).contiguous()
+    G, Cout, Cin = Wc.shape
+    per = int(lib.sonet_pointwise_tc_blob_bytes(Cout, Cin))
+    blob = torch.zeros(per * G, dtype=torch.uint8)
+    inv = ctypes.c_float(0.0)
+    _C.check(lib.sonet_pointwise_tc_pack_groups(Wc.data_ptr(), G, Cout, Cin, blob.data_ptr(),
+                                                ctypes.addressof(inv)),
+             "sonet_pointwise_tc_pack_groups")
+    return blob, per, float(inv.value)
+
+
+def upconv_im2col(x):
+    """x [B,Cin,H,W] -> xcol [4*B, 4*Cin, H*W]: the 2x2 low-resolution neighbourhoods of the four
+    output parities of a nearest-x2 + 3x3 up-convolution (csrc/upconv.cu)."""
+    _chk(x, "x", torch.float32)
+    B, Cin, H, W = x.shape
+    with torch.cuda.device(x.device):
+        xcol = torch.empty((4 * B, 4 * Cin, H * W), dtype=torch.float32, device=x.device)
+        _call("sonet_upconv_im2col_f32", _C.ptr(x), B, Cin, H, W, _C.ptr(xcol), _stream(x))
+    return xcol
+
+
+def pointwise_tc_grouped(x, blob, per_bytes, inv_scale, shift, cout, relu, groups, splits=1,
+                         scat_w=0, out=None, scratch=None):
+    """Grouped tcgen05 layer: x [G*B, C, P], G weight blobs -> out. scat_w = W > 0: the four groups
+    are the output parities of an up-convolution over [H, W] maps, interleaved into
+    out [B, cout, 4*P]; otherwise out [G*B, cout, P]. splits > 1: K split through `scratch`."""
+    _chk(x, "x", torch.float32)
+    _chk(blob, "blob", torch.uint8)
+    _chk(shift, "shift", torch.float32, optional=True)
+    GB, C, P = x.shape
+    B = GB // groups
+    dev = x.device
+    with torch.cuda.device(dev):
+        if scat_w > 0:
+            P_out, gstride = 4 * P, 0
+            if out is None:
+                out = torch.empty((B, cout, P_out), dtype=torch.float32, device=dev)
+        else:
+            P_out, gstride = P, B * cout * P
+            if out is None:
+                out = torch.empty((GB, cout, P), dtype=torch.float32, device=dev)
+        if splits > 1 and scratch is None:
+            scratch = torch.empty((groups * splits * B * cout * P,), dtype=torch.float32, device=dev)
+        _call("sonet_pointwise_tc_grouped_forward", _C.ptr(x), C, B, P, _C.ptr(blob), int(per_bytes),
+              float(inv_scale), _C.ptr(shift), int(cout), int(bool(relu)), int(groups), int(splits),
+              int(scat_w), int(P_out), int(gstride), _C.ptr(out), _C.ptr(scratch), _stream(x),
+              kernels=2 if splits > 1 else 1)
+    return out
+
+
 def pointwise_layer_tc(x0, blob, inv_scale, shift, cout, relu, x1=None, addend=None, gidx=None):
     """tcgen05 variant of pointwise_layer: x0 [B,C0,P] (+ x1) -> [B,cout,P]."""
     _chk(x0, "x0", torch.float32)

@@ -122,12 +122,10 @@ def test_autoencoder_vs_reference_golden():
     m.set_input(inp["pc"], inp["sn"], inp["label"], inp["node"], inp["node_knn_I"])
     m.test_model()
     _check_encoder_against_golden(g, m.encoder, opt)
-    # The decoder's 3x3 up-convolutions are PyTorch/cuDNN fp32 (out of the hot-path scope,
-    # SURVEY.md §2 row 9): six stacked convs over K = 9*C terms reassociate differently from the
-    # CPU reference's oneDNN, measured 1.4e-4 — compared at 5e-4. Everything in scope (encoder
-    # tensors above, Chamfer losses below) keeps the 1e-4 bar.
-    assert_golden(g, "predicted_pc", m.predicted_pc, tol=5e-4)
-    assert_golden(g, "conv_pc4", m.decoder.conv_pc4, tol=5e-4)
+    # the up-convolution decoder runs on the tcgen05 kernels (csrc/upconv.cu): 1e-4 like
+    # everything else (round 1 ran it through cuDNN and needed 5e-4)
+    assert_golden(g, "predicted_pc", m.predicted_pc)
+    assert_golden(g, "conv_pc4", m.decoder.conv_pc4)
     assert_close(m.loss_chamfer, g["loss_chamfer"], "loss_chamfer")
     assert_close(m.loss_chamfer_conv4, g["loss_chamfer_conv4"], "loss_chamfer_conv4")
     assert_close(m.loss, g["loss"], "loss")
@@ -275,8 +273,8 @@ def test_autoencoder_cfg4_full_size(oracle_mod):
     assert float(m.loss) == loss and torch.equal(arr, m.chamfer_criteria.loss_array)
     m.set_input(*[inp[k][:16] for k in keys])
     m.test_model()
-    # per-cloud losses are shard-consistent; not bit-exact because the out-of-scope decoder is
-    # PyTorch/cuDNN, whose conv algorithm choice depends on the batch size
+    # per-cloud losses are shard-consistent (the decoder's K split depends on the batch size, so
+    # the partial-sum grouping — not the order — differs: ~1e-7, not bit-exact)
     assert_close(m.chamfer_criteria.loss_array, arr[:16], "cfg-4 shard consistency", 1e-5)
     o = oracle_mod.chamfer(pred[:2].cpu(), inp["pc"][:2])
     assert_close(arr[:2], o["loss_array"], "cfg-4 chamfer loss_array slice vs oracle")
