@@ -48,6 +48,41 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// W % 4 == 0: a thread produces 4 consecutive pixels of one xcol row (one 16-byte store; the write
+// stream is what bounds this kernel — every input element is re-read 16 times, but from L1/L2).
+// blockDim = (TX, TY): TX threads cover the H*W/4 quads of a row, TY rows per block; a row is
+// (g, b, k) with k = t*Cin + ci.
+__global__ void __launch_bounds__(256)
+    upconv_im2col_vec4_kernel(const float* __restrict__ in, int B, int Cin, int H, int W,
+                              float* __restrict__ xcol) {
+  const int HW = H * W, K = 4 * Cin;
+  const int rows = 4 * B * K;
+  const int row = blockIdx.x * blockDim.y + threadIdx.y;
+  if (row >= rows) return;
+  const int k = row % K;
+  const int gb = row / K;
+  const int b = gb % B, g = gb / B;
+  const int t = k / Cin, ci = k - t * Cin;
+  const int dy = (t >> 1) - 1 + (g >> 1), dx = (t & 1) - 1 + (g & 1);
+  const float* src = in + (static_cast<size_t>(b) * Cin + ci) * HW;
+  float4* dst = reinterpret_cast<float4*>(xcol + static_cast<size_t>(row) * HW);
+  for (int q = threadIdx.x; q < (HW >> 2); q += blockDim.x) {
+    const int p = q << 2;
+    const int i = p / W, j = p - i * W;
+    const int y = i + dy;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y >= 0 && y < H) {
+      const float* r = src + y * W;
+      const int x = j + dx;
+      if (x >= 0) v.x = __ldg(r + x);          // x .. x+3 < W+1: only the ends can fall outside
+      v.y = __ldg(r + x + 1);
+      v.z = __ldg(r + x + 2);
+      if (x + 3 < W) v.w = __ldg(r + x + 3);
+    }
+    __stcs(dst + q, v);
+  }
+}
+
 }  // namespace sonet
 
 extern "C" int sonet_upconv_im2col_f32(const float* in, int B, int Cin, int H, int W, float* xcol,
@@ -57,6 +92,17 @@ extern "C" int sonet_upconv_im2col_f32(const float* in, int B, int Cin, int H, i
   if (B == 0) return SONET_OK;
   SONET_REQUIRE(in && xcol, "upconv_im2col: null pointer");
   const long long total = 16LL * B * Cin * H * W;
+  const long long rows = 16LL * B * Cin;
+  if (W % 4 == 0 && aligned16(xcol) && rows < (1LL << 31)) {
+    int tx = std::min(256, H * W / 4), ty = 1;
+    tx = std::max(tx, 1);
+    while (tx * ty * 2 <= 256) ty *= 2;
+    const long long blocks = (rows + ty - 1) / ty;
+    SONET_REQUIRE(blocks < (1LL << 31), "upconv_im2col: too many rows");
+    upconv_im2col_vec4_kernel<<<static_cast<unsigned>(blocks), dim3(tx, ty), 0, as_stream(stream)>>>(
+        in, B, Cin, H, W, xcol);
+    return check_launch("upconv_im2col");
+  }
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 16LL * sm_count()));
   upconv_im2col_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, B, Cin, H, W, xcol);
   return check_launch("upconv_im2col");

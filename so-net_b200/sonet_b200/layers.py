@@ -212,7 +212,11 @@ class _PointwiseConvBase(nn.Module):
         cin = x0.shape[1] + (0 if x1 is None else x1.shape[1])
         cout = self.conv.out_channels
         rows = x0.shape[0] * x0.shape[2]
-        if cin >= 32 and cout >= 64 and rows >= 1024 and os.environ.get("SONET_TC", "1") != "0":
+        # tcgen05 eligibility: a dense enough contraction (cin >= 32) over at least two 128-row
+        # tiles; thin OUTPUTS (the 128 -> 3 ConvToPC heads) qualify too — the layer is then a
+        # streaming read of the activations, which the TMA-fed kernel does at several times the
+        # rate of the register-tiled fp32 kernel
+        if cin >= 32 and rows >= 256 and os.environ.get("SONET_TC", "1") != "0":
             w, shift = self._folded.get(self._conv_weight2d(), self.conv.bias, norm,
                                         transpose=False)
             key = (self._folded.version, w.data_ptr())
