@@ -124,6 +124,42 @@ int sonet_pointwise_tc_grouped_forward(const float* x, int C, int B, int P, cons
                                        int P_out, long long out_gstride, float* out, float* scratch,
                                        sonet_stream_t stream);
 
+/* ---- f-2: train-mode kernels of the point-wise layers ---------------------------------------------
+ * EquivariantLayer in train() mode = Conv1d(k=1) -> MyBatchNorm1d with BATCH statistics
+ * (models/layers.py:22-70, 282-296) -> ReLU, and its backward; the backward of the per-node pool
+ * (the gather of models/networks.py:185).
+ *   sonet_bn_train_forward_f32: x [B,C,P] -> per-channel batch mean / biased variance / invstd
+ *     (two-stage, fp64 partial sums in a fixed order: bit-reproducible) and
+ *     y = act(gamma*(x-mean)*invstd + beta) in one elementwise pass. partial: scratch of
+ *     sonet_bn_partial_slots(B,C) doubles. (The running-statistics update with the reference's
+ *     momentum schedule stays on the host side: two [C] vector ops.)
+ *   sonet_bn_train_backward_f32: dy, x (the BN input) -> dx, dgamma, dbeta; with relu the gate is
+ *     recomputed from x (gamma*xhat+beta > 0), so the forward output need not be kept.
+ *   sonet_index_max_backward_f32: grad_data [B,C,N] = 0; grad_data[b,c,idx[b,c,k]] += grad_out[b,c,k]
+ *     (k ascending, one thread per (b,c): deterministic also when empty nodes all gather point 0).
+ *   sonet_pointwise_tc_pack_device: fp32 W [Cout,Cin] on the DEVICE -> tcgen05 blob (optionally of
+ *     W^T, for the dgrad GEMM) with the power-of-two pre-scale computed on the device;
+ *     scale2[0]=scale, scale2[1]=1/scale; scratch_bits: one uint32 of scratch.
+ *   sonet_pointwise_tc_forward_dev: the generic tcgen05 layer with that blob (1/scale read from
+ *     device memory): the forward GEMM y = W x + b and the dgrad GEMM dx = W^T dy of a training step.
+ * The wgrad GEMM dW = dy x^T (contraction over points) is not part of this library yet. */
+int sonet_bn_partial_slots(int B, int C);
+int sonet_bn_train_forward_f32(const float* x, const float* gamma, const float* beta, int B, int C,
+                               int P, float eps, int relu, double* partial, float* y,
+                               float* save_mean, float* save_var, float* save_invstd,
+                               sonet_stream_t stream);
+int sonet_bn_train_backward_f32(const float* dy, const float* x, const float* mean,
+                                const float* invstd, const float* gamma, const float* beta, int B,
+                                int C, int P, int relu, double* partial, float* dx, float* dgamma,
+                                float* dbeta, sonet_stream_t stream);
+int sonet_index_max_backward_f32(const float* grad_out, const int32_t* idx, int B, int C, int N, int K,
+                                 float* grad_data, sonet_stream_t stream);
+int sonet_pointwise_tc_pack_device(const float* W, int Cout, int Cin, int transpose, void* blob,
+                                   float* scale2, unsigned* scratch_bits, sonet_stream_t stream);
+int sonet_pointwise_tc_forward_dev(const float* x0, int C0, int B, int P, const void* blob,
+                                   const float* inv_scale_dev, const float* shift, int Cout, int relu,
+                                   float* out, sonet_stream_t stream);
+
 /* ---- f-4: batch-SOM training --------------------------------------------------------------------
  * Replaces BatchSOM.batch_update / BatchSOM.optimize (util/som.py:295-366): T iterations of
  * {nearest-node assignment, per-node mean, neighbourhood-weighted node update} per cloud, in ONE

@@ -73,6 +73,8 @@ struct Dims {
   int scat_w;    // > 0: group g = (py, px) parity of a x2 up-convolution over a [*, scat_w] map;
                  //      row p = i*W + j is stored at (2i+py)*2W + 2j+px of a [B, Cout, P_out] map
   int P_out;     // point stride of `out` (= P unless scattering)
+  const float* inv_ptr;     // non-null: 1 / weight pre-scale lives in device memory (train mode:
+                            // the weights are packed on the device every step, csrc/train.cu)
   long long blob_gstride;   // bytes between the weight blobs of consecutive groups
   long long out_gstride;    // floats between the outputs of consecutive groups (0 when scattering)
   long long out_sstride;    // floats between the partial sums of consecutive K splits
@@ -382,6 +384,7 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
     const int m = q4 * 32 + lane;
     const uint32_t lane_base = tm + (static_cast<uint32_t>(q4 * 32) << 16);
     const float floor_v = d.relu ? 0.f : -__int_as_float(0x7f800000);   // ReLU as one max
+    const float inv_w = d.inv_ptr != nullptr ? __ldg(d.inv_ptr) : d.inv;
     for (int it = 0; it < my_items; ++it) {
       const Item im = decode_item(d, blockIdx.x + it * gridDim.x);
       const int nt = im.nt;
@@ -455,7 +458,7 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               if (all_real || cg + i0 + i < d.Cout) {
-                const float y = fmaf(__uint_as_float(v[i]), d.inv, sh[i0 + i]) + ad[i];
+                const float y = fmaf(__uint_as_float(v[i]), inv_w, sh[i0 + i]) + ad[i];
                 o[static_cast<size_t>(i0 + i) * d.P_out] = fmaxf(y, floor_v);
               }
             }
@@ -589,6 +592,7 @@ static bool make_activation_map(CUtensorMap* m, const float* x, int B, int C, in
 
 struct TcExt {   // grouped / split-K / scatter launch options (defaults = the plain layer)
   int groups = 1, splits = 1, scat_w = 0, P_out = 0;
+  const float* inv_ptr = nullptr;
   long long blob_gstride = 0, out_gstride = 0, out_sstride = 0;
 };
 
@@ -626,6 +630,7 @@ static int launch_pointwise_tc(const float* x0, int C0, const float* x1, int C1,
   d.kpi = d.kchunks / ext.splits;
   d.scat_w = ext.scat_w;
   d.P_out = ext.P_out > 0 ? ext.P_out : P;
+  d.inv_ptr = ext.inv_ptr;
   d.blob_gstride = ext.blob_gstride;
   d.out_gstride = ext.out_gstride;
   d.out_sstride = ext.out_sstride;
@@ -717,6 +722,20 @@ extern "C" int sonet_pointwise_tc_grouped_forward(const float* x, int C, int B, 
   splitk_reduce_kernel<<<grid, 256, 0, as_stream(stream)>>>(scratch, groups, splits, B, Cout, P, shift,
                                                             relu, scat_w, P_out, out_gstride, out);
   return check_launch("splitk_reduce");
+}
+
+// Train-mode variant: the weight blob was packed on the device this step
+// (sonet_pointwise_tc_pack_device) and its 1/pre-scale is read from device memory.
+extern "C" int sonet_pointwise_tc_forward_dev(const float* x0, int C0, int B, int P, const void* blob,
+                                              const float* inv_scale_dev, const float* shift,
+                                              int Cout, int relu, float* out,
+                                              sonet_stream_t stream) {
+  using namespace sonet;
+  SONET_REQUIRE(inv_scale_dev != nullptr, "pointwise_tc_forward_dev: null inv_scale pointer");
+  TcExt e;
+  e.inv_ptr = inv_scale_dev;
+  return launch_pointwise_tc(x0, C0, nullptr, 0, B, P, blob, 1.f, shift, Cout, relu, nullptr, nullptr,
+                             0, out, nullptr, stream, e);
 }
 
 extern "C" int sonet_debug_pointwise_tc_timeline(const float* x0, int C0, int B, int P,

@@ -31,6 +31,18 @@ _SIGNATURES = {
                                            ctypes.c_longlong, ctypes.c_float, c_void_p, c_int, c_int,
                                            c_int, c_int, c_int, c_int, ctypes.c_longlong, c_void_p,
                                            c_void_p, c_void_p],
+    "sonet_bn_partial_slots": [c_int, c_int],
+    "sonet_bn_train_forward_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_float,
+                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sonet_bn_train_backward_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                    c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p],
+    "sonet_index_max_backward_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                     c_void_p],
+    "sonet_pointwise_tc_pack_device": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_void_p],
+    "sonet_pointwise_tc_forward_dev": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_int, c_int, c_void_p, c_void_p],
     "sonet_som_train": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                         c_void_p, c_void_p, c_void_p],
     "sonet_augment_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -20,7 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch.nn.modules.batchnorm import _BatchNorm
 
-from . import operations, ops
+from . import operations, ops, train_ops
 
 
 # Set to True to make eval-mode forwards differentiable w.r.t. the parameters as well (the
@@ -204,6 +204,12 @@ class _PointwiseConvBase(nn.Module):
                 and all(p == 0 for p in self.conv.padding)
                 and self.normalization in (None, 'batch') and self.activation in (None, 'relu'))
 
+    def _train_kernels(self, x):
+        """train() mode on CUDA fp32 with the default norm/activation: the sm_100a train kernels
+        (train_ops) instead of the PyTorch composition."""
+        return (train_ops.ENABLED and self.training and torch.is_grad_enabled() and x.is_cuda
+                and x.dtype == torch.float32 and self._fast_eligible())
+
     def forward_points(self, x0, x1=None, addend=None, gidx=None):
         """x0 [B,C0,P] (+ x1 [B,C1,P] virtually concatenated on channels) -> [B,Cout,P].
         Dense layers run on tcgen05 (csrc/pointwise_tc.cu, fp16 hi/lo split); thin ones on the
@@ -268,6 +274,12 @@ class MyConv2d(_PointwiseConvBase):
         if _fast_ok(self, x) and x.dim() == 4 and self._fast_eligible():
             B, C, H, W = x.shape
             y = self.forward_points(x.contiguous().view(B, C, H * W))
+            return y.view(B, y.shape[1], H, W)
+        if x.dim() == 4 and self._train_kernels(x):
+            B, C, H, W = x.shape
+            y = train_ops.conv_bn_act_train(
+                x.contiguous().view(B, C, H * W), self._conv_weight2d(), self.conv.bias,
+                self.norm if self.normalization == 'batch' else None, self.activation == 'relu', epoch)
             return y.view(B, y.shape[1], H, W)
         # PyTorch/cuDNN path (3x3 decoder convs, training): strict fp32 — cuDNN's default TF32
         # convolution is ~1e-3 relative, outside the 1e-4 parity bar of the reference's fp32 math
@@ -441,6 +453,10 @@ class EquivariantLayer(_PointwiseConvBase):
     def forward(self, x, epoch=None):
         if self.fast(x) and x.dim() == 3:
             return self.forward_points(x.contiguous())
+        if self._train_kernels(x) and x.dim() == 3:
+            return train_ops.conv_bn_act_train(
+                x, self._conv_weight2d(), self.conv.bias,
+                self.norm if self.normalization == 'batch' else None, self.activation == 'relu', epoch)
         y = self.conv(x)
         if self.normalization == 'batch':
             y = self.norm(y, epoch)

@@ -17,7 +17,7 @@ import os
 import torch
 import torch.nn as nn
 
-from . import ops, som
+from . import ops, som, train_ops
 from .layers import (EquivariantLayer, KNNModule, MyConv2d, MyLinear, PointNet, PointResNet,
                      UpConv, _fast_ok)
 
@@ -211,9 +211,15 @@ class Encoder(nn.Module):
             x_in = torch.cat((x_dec, torch.cat((sn,) * k, dim=2)), dim=1) if use_sn else x_dec
             self._x_aug = x_in
             self._first_pn_out = self.first_pointnet(x_in, epoch)
-            gather_index = ops.index_max(self._first_pn_out.detach().contiguous(), idx32, M).long()
-            self.first_pn_out_masked_max = self._first_pn_out.gather(
-                dim=2, index=gather_index * mask_row_max.unsqueeze(1).long())
+            if train_ops.ENABLED:
+                # arg-max kernel forward (values fused) + deterministic scatter backward
+                self.first_pn_out_masked_max = train_ops.IndexMaxGather.apply(
+                    self._first_pn_out, idx32, M)
+            else:
+                gather_index = ops.index_max(self._first_pn_out.detach().contiguous(), idx32,
+                                             M).long()
+                self.first_pn_out_masked_max = self._first_pn_out.gather(
+                    dim=2, index=gather_index * mask_row_max.unsqueeze(1).long())
 
         if opt.som_k >= 2:
             if pooled is None:

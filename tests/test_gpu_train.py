@@ -1,0 +1,129 @@
+"""-m gpu: train-mode kernels (csrc/train.cu, sonet_b200/train_ops.py) against
+the PyTorch composition the reference trains with (conv1d -> batch_norm(training=True) -> relu,
+gather; models/layers.py:22-70, 282-296, models/networks.py:185). Tolerance: |a-b| <= tol * max|b|
+per tensor (gradients have no natural unit scale)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def close(a, b, what, tol=1e-4):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    scale = float(b.abs().max().clamp(min=1e-12))
+    err = float((a - b).abs().max()) / scale
+    assert err <= tol, "%s: max|a-b|/max|b| = %.3e > %.1e" % (what, err, tol)
+
+
+@pytest.mark.parametrize("B,C,P,relu", [(4, 64, 3000, True), (2, 384, 777, True), (3, 40, 1, False),
+                                        (64, 128, 576, True)])
+def test_bn_act_train_forward_backward_vs_torch(B, C, P, relu):
+    from sonet_b200 import train_ops
+    g = torch.Generator().manual_seed(B * C + P)
+    x = (torch.randn(B, C, P, generator=g) * 2 + 0.5).to(DEV).requires_grad_(True)
+    gamma = (torch.rand(C, generator=g) + 0.5).to(DEV).requires_grad_(True)
+    beta = (torch.randn(C, generator=g) * 0.2).to(DEV).requires_grad_(True)
+    w = torch.randn(B, C, P, generator=g).to(DEV)
+    y, mean, var = train_ops.BNActTrain.apply(x, gamma, beta, 1e-5, relu)
+    (y * w).sum().backward()
+    got = [t.grad.clone() for t in (x, gamma, beta)]
+    for t in (x, gamma, beta):
+        t.grad = None
+    yr = F.batch_norm(x, None, None, gamma, beta, True, 0.1, 1e-5)
+    yr = F.relu(yr) if relu else yr
+    (yr * w).sum().backward()
+    close(y, yr, "y", 1e-5)
+    close(mean, x.detach().mean(dim=(0, 2)), "mean", 1e-5)
+    close(var, x.detach().var(dim=(0, 2), unbiased=False), "var", 1e-5)
+    for a, t, n in zip(got, (x, gamma, beta), ("dx", "dgamma", "dbeta")):
+        close(a, t.grad, n, 2e-4)
+    # bit-reproducible
+    y2, _, _ = train_ops.BNActTrain.apply(x.detach(), gamma.detach(), beta.detach(), 1e-5, relu)
+    assert torch.equal(y2, y.detach())
+
+
+@pytest.mark.parametrize("B,cin,cout,P", [(4, 64, 128, 1500), (2, 320, 384, 1024), (64, 387, 512, 576)])
+def test_conv_tc_forward_dgrad_vs_torch(B, cin, cout, P):
+    from sonet_b200 import train_ops
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(B, cin, P, generator=g).to(DEV).requires_grad_(True)
+    W = (torch.randn(cout, cin, generator=g) * (2.0 / cin) ** 0.5).to(DEV).requires_grad_(True)
+    b = (torch.randn(cout, generator=g) * 0.1).to(DEV).requires_grad_(True)
+    w = torch.randn(B, cout, P, generator=g).to(DEV)
+    y = train_ops.ConvTC.apply(x, W, b)
+    (y * w).sum().backward()
+    got = [t.grad.clone() for t in (x, W, b)]
+    for t in (x, W, b):
+        t.grad = None
+    yr = F.conv1d(x.double(), W.double().unsqueeze(2), b.double())
+    (yr * w.double()).sum().backward()
+    close(y, yr, "y")
+    for a, t, n in zip(got, (x, W, b), ("dx", "dW", "db")):
+        close(a, t.grad, n)
+
+
+def test_index_max_gather_backward_vs_torch_gather(oracle_mod):
+    from sonet_b200 import train_ops
+    rs = np.random.RandomState(4)
+    B, C, N, K = 3, 37, 999, 64
+    data = torch.from_numpy(rs.normal(size=(B, C, N)).astype(np.float32)).to(DEV).requires_grad_(True)
+    index = torch.from_numpy(rs.randint(0, K, size=(B, N)).astype(np.int32))
+    index[index == 5] = 6                                   # empty nodes: they all gather point 0
+    index[index == 17] = 18
+    index = index.to(DEV)
+    w = torch.from_numpy(rs.normal(size=(B, C, K)).astype(np.float32)).to(DEV)
+    out = train_ops.IndexMaxGather.apply(data, index, K)
+    (out * w).sum().backward()
+    got = data.grad.clone()
+    data.grad = None
+    gi = oracle_mod.index_max(data.detach().cpu(), index.cpu(), K).long().to(DEV)
+    ref = data.gather(2, gi)                                # idx is already 0 for empty nodes
+    (ref * w).sum().backward()
+    assert torch.equal(out.detach(), ref.detach())
+    close(got, data.grad, "d data", 1e-6)
+    assert float(got[:, :, 0].abs().sum()) > 0              # the empty nodes' gradient landed on point 0
+
+
+def test_classifier_training_step_kernels_vs_torch_composition():
+    """One optimize() step from identical weights with the train kernels ON and OFF: same loss,
+    same gradients (1e-3 of each tensor's scale: the tcgen05 GEMMs carry ~1e-5 per layer),
+    same running statistics."""
+    from helpers import build_states
+    from sonet_b200 import classifier, synth, train_ops
+    opt = synth.make_opt("classifier", batch_size=8, input_pc_num=512, device=DEV)
+    opt.device = torch.device(DEV)
+    st = build_states("classifier", opt, seed=81)
+    inp = synth.synth_inputs(8, 512, seed=81)
+    res = {}
+    for flag in (True, False):
+        train_ops.ENABLED = flag
+        try:
+            m = classifier.Model(opt)
+            m.encoder.load_state_dict(st["encoder"])
+            m.classifier.load_state_dict(st["head"])
+            m.set_input(inp["pc"], inp["sn"], inp["label"], inp["node"], inp["node_knn_I"])
+            m.encoder.train()
+            m.classifier.train()
+            torch.manual_seed(0)                              # dropout masks
+            m.forward(is_train=True, epoch=3)
+            loss = m.softmax_criteria(m.score, m.label)
+            m.encoder.zero_grad()
+            m.classifier.zero_grad()
+            loss.backward()
+            res[flag] = dict(
+                loss=loss.detach().clone(),
+                grads={n: p.grad.detach().clone() for n, p in m.encoder.named_parameters()
+                       if p.grad is not None},
+                rm=m.encoder.first_pointnet.layers[1].norm.running_mean.clone(),
+                rv=m.encoder.first_pointnet.layers[1].norm.running_var.clone())
+        finally:
+            train_ops.ENABLED = True
+    close(res[True]["loss"], res[False]["loss"], "loss", 1e-4)
+    close(res[True]["rm"], res[False]["rm"], "running_mean", 1e-5)
+    close(res[True]["rv"], res[False]["rv"], "running_var", 1e-5)
+    assert set(res[True]["grads"]) == set(res[False]["grads"]) and len(res[True]["grads"]) > 20
+    for n, gref in res[False]["grads"].items():
+        close(res[True]["grads"][n], gref, "grad " + n, 2e-3)
