@@ -435,6 +435,9 @@ def main():
     ap.add_argument("--impl", default="sonet_b200", choices=["sonet_b200", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS),
                     help="BASELINE.json config (cfg2 = configs[1], the headline)")
+    ap.add_argument("--collective", default="torch", choices=["torch", "sonet"],
+                    help="N>1: all-gather through torch.distributed (NCCL) or through the C-ABI "
+                         "sonet_allgather (the same NCCL, resolved by libsonet_b200)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager op calls instead of CUDA-graph replay")
     args = ap.parse_args()
@@ -484,10 +487,8 @@ def main():
     model.test_model()
     row_shape = tuple(result_rows(task, model).shape[1:])
     d2h_bytes = B * int(torch.tensor(row_shape).prod()) * 4
-    stage = [torch.empty((B,) + row_shape, dtype=torch.float32, device=dev) for _ in range(2)]
-    gathered = [torch.empty((total_rows,) + row_shape, dtype=torch.float32, device=dev)
-                for _ in range(2)] if world > 1 else None
-    pending = [None, None]
+    ag = sdist.AsyncGather(world, (B,) + row_shape, dev, impl=args.collective) if world > 1 else None
+    gathered = ag.out if ag else None
 
     def gpu_step(i):
         """Forward i; its result rows are staged (the graph's static buffer is overwritten by the
@@ -497,19 +498,13 @@ def main():
         rows = result_rows(task, model)
         if world == 1:
             return rows
-        stage[i & 1].copy_(rows)
-        pending[i & 1] = dist.all_gather_into_tensor(gathered[i & 1], stage[i & 1], async_op=True)
-        prev = pending[(i - 1) & 1]
-        if prev is not None:
-            prev.wait()
-            pending[(i - 1) & 1] = None
-        return gathered[i & 1]
+        o = ag.launch(i, rows)
+        ag.wait_prev(i)
+        return o
 
     def drain():
-        for j in (0, 1):
-            if pending[j] is not None:
-                pending[j].wait()
-                pending[j] = None
+        if ag:
+            ag.drain()
 
     # ---- (1) device-resident arm -------------------------------------------------------------------
     torch.cuda.synchronize()
@@ -666,8 +661,8 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": cfg["workload"], "name": args.config,
                            "global_batch": total_rows,
-                           "parallelism": "dp%d batch-sharded, 1 async all-gather of the result rows/step"
-                                          % world,
+                           "parallelism": "dp%d batch-sharded, 1 async all-gather of the result rows/step "
+                                          "(%s)" % (world, args.collective),
                            "l2": "256 MB flush write between timed steps (outside event pairs)",
                            "weights": "random (seeded), BN stats randomised",
                            "launch": "eager" if args.no_graph else

@@ -97,6 +97,23 @@ int sonet_som_decenter(const float* x, const float* sn, const float* cluster_mea
                        const int32_t* min_idx_i32, int B, int N, int M, int k,
                        float* centers, float* x_aug, sonet_stream_t stream);
 
+/* ---- e: the path's collective ------------------------------------------------------------------------
+ * The eval forward shards over the batch with no exchange inside the path; the
+ * one collective is an all-gather of the per-shard result rows (logits [B/G, classes], per-cloud
+ * losses) over NCCL/NVLink. NCCL is resolved from the running process (dlopen libnccl.so.2), so
+ * the library itself links only libcudart.
+ *   sonet_comm_unique_id: rank 0 fills a 128-byte NCCL unique id; the host program distributes it.
+ *   sonet_comm_init: ncclCommInitRank on the CURRENT device -> opaque communicator.
+ *   sonet_allgather: recv[r*bytes .. (r+1)*bytes) = rank r's send buffer, asynchronous on `stream`,
+ *     CUDA-graph capturable; in-place (send == recv + rank*bytes) allowed.
+ *   sonet_comm_nccl_version: NCCL version code, 0 when NCCL cannot be loaded. */
+int sonet_comm_nccl_version(void);
+int sonet_comm_unique_id(void* id128);
+int sonet_comm_init(const void* id128, int rank, int world, void** comm_out);
+int sonet_allgather(void* comm, const void* send, void* recv, long long bytes_per_rank,
+                    sonet_stream_t stream);
+int sonet_comm_destroy(void* comm);
+
 /* ---- f-1: the auto-encoder's up-convolution decoder -------------------------------------------
  * Replaces UpConv.forward (models/layers.py:214-240; DecoderConv, models/networks.py:394-431):
  * nearest x2 up-sampling + 3x3 convolution (pad 1) + eval BatchNorm + ReLU, computed as four

@@ -70,7 +70,7 @@ def build(force=False, verbose=False):
             for s in ex.map(compile_one, jobs):
                 print("[build] compiled", os.path.relpath(s, HERE))
     if jobs or not os.path.exists(LIB):
-        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart", "-lpthread"]
+        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart", "-lpthread", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

@@ -34,17 +34,19 @@ constexpr int ST_THREADS = 1024;
 constexpr int ST_WARPS = ST_THREADS / 32;
 constexpr int ST_MAX_M = 256;
 
-// smem: nodes as float4 [M] | mean float [3][M] + occupied [M] | x [3][N] (optional) | idx u8 [N]
+// smem: nodes as float4 [M] | mean float [3][M] + occupied [M] | W_t [M][M] (optional) |
+//       x [3][N] (optional) | idx u8 [N]
 __global__ void __launch_bounds__(ST_THREADS, 1)
     som_train_kernel(const float* __restrict__ x, const float* __restrict__ node_init,
                      int node_init_batched, const float* __restrict__ weights,
-                     const float* __restrict__ lr, int T, int N, int M, int x_in_smem,
+                     const float* __restrict__ lr, int T, int N, int M, int x_in_smem, int w_in_smem,
                      float* __restrict__ node_out, int32_t* __restrict__ idx_out) {
   extern __shared__ __align__(16) unsigned char st_smem[];
   float4* snode = reinterpret_cast<float4*>(st_smem);                  // [M]
   float* smean = reinterpret_cast<float*>(snode + M);                  // [3][M]
   float* socc = smean + 3 * M;                                         // [M]
-  float* sx = socc + M;                                                // [3][N] when x_in_smem
+  float* sw = socc + M;                                                // [M][M] when w_in_smem
+  float* sx = sw + (w_in_smem ? M * M : 0);                            // [3][N] when x_in_smem
   unsigned char* sidx =
       reinterpret_cast<unsigned char*>(sx + (x_in_smem ? 3 * static_cast<size_t>(N) : 0));
 
@@ -59,6 +61,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
   __syncthreads();
 
   for (int t = 0; t < T; ++t) {
+    // this iteration's neighbourhood weights: issued now, consumed in step 3 — the 64 dependent-
+    // latency L2 reads per thread of the first version cost more than the assignment
+    if (w_in_smem) {
+      const float* Wg = weights + static_cast<size_t>(t) * M * M;
+      for (int i = tid; i < M * M; i += ST_THREADS) sw[i] = __ldg(Wg + i);
+    }
     // ---- 1. assignment ----------------------------------------------------------------------
     for (int n0 = tid; n0 < N; n0 += 2 * ST_THREADS) {
       const int n1 = n0 + ST_THREADS;
@@ -114,7 +122,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
     __syncthreads();
 
     // ---- 3. node update: thread per (c, j) ----------------------------------------------------
-    const float* W = weights + static_cast<size_t>(t) * M * M;   // W[m][j]
+    const float* W = w_in_smem ? sw : weights + static_cast<size_t>(t) * M * M;   // W[m][j]
     const float lrt = __ldg(lr + t);
     float newv = 0.f;
     const bool upd = tid < 3 * M;
@@ -125,7 +133,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
       double acc = 0.0;
       for (int m = 0; m < M; ++m) {
         const float diff = __fmul_rn(__fsub_rn(smean[c * M + m], nj), socc[m]);
-        const float term = __fmul_rn(__fmul_rn(diff, __ldg(W + static_cast<size_t>(m) * M + j)), lrt);
+        const float term = __fmul_rn(__fmul_rn(diff, W[static_cast<size_t>(m) * M + j]), lrt);
         acc += static_cast<double>(term);
       }
       newv = __fadd_rn(nj, static_cast<float>(acc));
@@ -158,7 +166,9 @@ extern "C" int sonet_som_train(const float* x, const float* node_init, int node_
   SONET_REQUIRE(M >= 1 && M <= ST_MAX_M, "som_train: M=%d out of range [1,%d]", M, ST_MAX_M);
   if (B == 0) return SONET_OK;
   SONET_REQUIRE(x && node_init && node_out && (T == 0 || (weights && lr)), "som_train: null pointer");
-  const size_t fixed = sizeof(float4) * M + sizeof(float) * 4 * M;
+  const int w_in_smem = (static_cast<size_t>(M) * M * sizeof(float) <= 64 * 1024) ? 1 : 0;
+  const size_t fixed = sizeof(float4) * M + sizeof(float) * 4 * M +
+                       (w_in_smem ? sizeof(float) * M * M : 0);
   const size_t with_x = fixed + sizeof(float) * 3 * static_cast<size_t>(N) + static_cast<size_t>(N) + 16;
   const size_t without_x = fixed + static_cast<size_t>(N) + 16;
   const size_t cap = static_cast<size_t>(max_smem_optin());
@@ -169,6 +179,6 @@ extern "C" int sonet_som_train(const float* x, const float* node_init, int node_
   cudaFuncSetAttribute(som_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        static_cast<int>(smem));
   som_train_kernel<<<B, ST_THREADS, smem, as_stream(stream)>>>(
-      x, node_init, node_init_batched, weights, lr, T, N, M, x_in_smem, node_out, last_idx);
+      x, node_init, node_init_batched, weights, lr, T, N, M, x_in_smem, w_in_smem, node_out, last_idx);
   return check_launch("som_train");
 }

@@ -43,6 +43,11 @@ _SIGNATURES = {
                                        c_void_p],
     "sonet_pointwise_tc_forward_dev": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                        c_int, c_int, c_void_p, c_void_p],
+    "sonet_comm_nccl_version": [],
+    "sonet_comm_unique_id": [c_void_p],
+    "sonet_comm_init": [c_void_p, c_int, c_int, c_void_p],
+    "sonet_allgather": [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p],
+    "sonet_comm_destroy": [c_void_p],
     "sonet_som_train": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                         c_void_p, c_void_p, c_void_p],
     "sonet_augment_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,

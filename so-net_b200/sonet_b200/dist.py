@@ -75,3 +75,94 @@ class ShardedForward:
         lo, hi = shard_bounds(total_rows, self.rank, self.world)
         shard = {k: v[lo:hi] for k, v in global_inputs.items()}
         return all_gather_rows(self.forward_fn(shard), total_rows)
+
+
+class SonetComm:
+    """The C-ABI collective (sonet_comm_init / sonet_allgather, csrc/comm.cu): an NCCL communicator
+    created through libsonet_b200 on the current device. torch.distributed must be initialised
+    (any backend): its process group is only the transport of the 128-byte unique id."""
+
+    def __init__(self):
+        import ctypes
+        from . import _C
+        self._C = _C
+        rank, world = dist.get_rank(), dist.get_world_size()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            _C.check(_C.lib().sonet_comm_unique_id(idt.data_ptr()), "sonet_comm_unique_id")
+        idt = idt.to(dev) if dist.get_backend() == "nccl" else idt
+        dist.broadcast(idt, src=0)
+        idt = idt.cpu().contiguous()
+        handle = ctypes.c_void_p()
+        _C.check(_C.lib().sonet_comm_init(idt.data_ptr(), rank, world, ctypes.byref(handle)),
+                 "sonet_comm_init")
+        self.handle, self.rank, self.world = handle, rank, world
+
+    def all_gather(self, local, out, stream=None):
+        """out [world*rows, ...] <- every rank's local [rows, ...]; asynchronous on `stream`
+        (default: the current stream); CUDA-graph capturable."""
+        local = local.contiguous()
+        st = (stream or torch.cuda.current_stream(local.device)).cuda_stream
+        self._C.check(self._C.lib().sonet_allgather(self.handle, local.data_ptr(), out.data_ptr(),
+                                                    local.numel() * local.element_size(), st),
+                      "sonet_allgather")
+        return out
+
+    def destroy(self):
+        if self.handle:
+            self._C.check(self._C.lib().sonet_comm_destroy(self.handle), "sonet_comm_destroy")
+            self.handle = None
+
+
+class AsyncGather:
+    """Per-step all-gather of result rows that completes under the NEXT step's forward.
+
+    launch(i, rows): stage the rows (a graph's static output buffer is overwritten by the next
+    replay) and start the gather of step i; wait_prev(i): make the current stream wait for the
+    gather of step i-1 — called at the end of step i, so every gather ends inside a step.
+    impl 'torch': torch.distributed.all_gather_into_tensor(async_op=True) (NCCL's own stream);
+    impl 'sonet': sonet_allgather on a side stream ordered by events."""
+
+    def __init__(self, world, rows_shape, dev, impl="torch"):
+        self.world, self.impl, self.dev = world, impl, dev
+        self.stage = [torch.empty(rows_shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        full = (rows_shape[0] * world,) + tuple(rows_shape[1:])
+        self.out = [torch.empty(full, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.pending = [None, None]
+        if impl == "sonet":
+            self.comm = SonetComm()
+            self.side = torch.cuda.Stream(device=dev)
+            self.ev_fwd = [torch.cuda.Event(), torch.cuda.Event()]
+            self.ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def launch(self, i, rows):
+        j = i & 1
+        self.stage[j].copy_(rows)
+        if self.impl == "torch":
+            self.pending[j] = dist.all_gather_into_tensor(self.out[j], self.stage[j], async_op=True)
+        else:
+            cur = torch.cuda.current_stream(self.dev)
+            self.ev_fwd[j].record(cur)
+            self.side.wait_event(self.ev_fwd[j])
+            self.comm.all_gather(self.stage[j], self.out[j], stream=self.side)
+            self.ev_done[j].record(self.side)
+            self.pending[j] = self.ev_done[j]
+        return self.out[j]
+
+    def _wait(self, j):
+        p = self.pending[j]
+        if p is None:
+            return
+        if self.impl == "torch":
+            p.wait()
+        else:
+            torch.cuda.current_stream(self.dev).wait_event(p)
+        self.pending[j] = None
+
+    def wait_prev(self, i):
+        self._wait((i - 1) & 1)
+
+    def drain(self):
+        self._wait(0)
+        self._wait(1)

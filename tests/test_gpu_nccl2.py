@@ -53,7 +53,13 @@ def _worker(rank, world, port, B, N, q):
         m.set_input(*[inp[k][lo:hi] for k in keys])
         m.test_model()
     out = sdist.all_gather_rows(m.score, B)
+    # the C-ABI collective (sonet_comm_init / sonet_allgather): same rows, bit for bit
+    comm = sdist.SonetComm()
+    out2 = torch.empty_like(out)
+    comm.all_gather(m.score, out2)
     torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    comm.destroy()
     if rank == 0:
         q.put(out.cpu())
     dist.barrier()
