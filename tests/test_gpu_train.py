@@ -98,6 +98,11 @@ def test_classifier_training_step_kernels_vs_torch_composition():
     st = build_states("classifier", opt, seed=81)
     inp = synth.synth_inputs(8, 512, seed=81)
     res = {}
+    # the PyTorch composition must be a strict-fp32 baseline: cuDNN/cuBLAS default to TF32
+    # (~1e-3), which is coarser than the kernels under test
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     for flag in (True, False):
         train_ops.ENABLED = flag
         try:
@@ -121,6 +126,7 @@ def test_classifier_training_step_kernels_vs_torch_composition():
                 rv=m.encoder.first_pointnet.layers[1].norm.running_var.clone())
         finally:
             train_ops.ENABLED = True
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     close(res[True]["loss"], res[False]["loss"], "loss", 1e-4)
     close(res[True]["rm"], res[False]["rm"], "running_mean", 1e-5)
     close(res[True]["rv"], res[False]["rv"], "running_var", 1e-5)
