@@ -132,4 +132,9 @@ def test_classifier_training_step_kernels_vs_torch_composition():
     close(res[True]["rv"], res[False]["rv"], "running_var", 1e-5)
     assert set(res[True]["grads"]) == set(res[False]["grads"]) and len(res[True]["grads"]) > 20
     for n, gref in res[False]["grads"].items():
-        close(res[True]["grads"][n], gref, "grad " + n, 2e-3)
+        if float(gref.abs().max()) < 1e-6:
+            # a conv bias in front of a batch-stat BN: its gradient is analytically zero, both
+            # paths return rounding noise
+            assert float(res[True]["grads"][n].abs().max()) < 1e-5, n
+        else:
+            close(res[True]["grads"][n], gref, "grad " + n, 2e-3)
