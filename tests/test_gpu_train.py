@@ -132,9 +132,12 @@ def test_classifier_training_step_kernels_vs_torch_composition():
     close(res[True]["rv"], res[False]["rv"], "running_var", 1e-5)
     assert set(res[True]["grads"]) == set(res[False]["grads"]) and len(res[True]["grads"]) > 20
     for n, gref in res[False]["grads"].items():
-        if float(gref.abs().max()) < 1e-6:
+        prefix = n.rsplit(".", 2)[0]
+        if n.endswith("conv.bias") and prefix + ".norm.weight" in res[False]["grads"]:
             # a conv bias in front of a batch-stat BN: its gradient is analytically zero, both
-            # paths return rounding noise
-            assert float(res[True]["grads"][n].abs().max()) < 1e-5, n
+            # paths return rounding noise — negligible against the weight gradient of the layer
+            wscale = float(res[False]["grads"][prefix + ".conv.weight"].abs().max())
+            assert float(res[True]["grads"][n].abs().max()) < 1e-3 * wscale, n
+            assert float(gref.abs().max()) < 1e-3 * wscale, n
         else:
             close(res[True]["grads"][n], gref, "grad " + n, 2e-3)
