@@ -132,12 +132,15 @@ def test_classifier_training_step_kernels_vs_torch_composition():
     close(res[True]["rv"], res[False]["rv"], "running_var", 1e-5)
     assert set(res[True]["grads"]) == set(res[False]["grads"]) and len(res[True]["grads"]) > 20
     for n, gref in res[False]["grads"].items():
-        prefix = n.rsplit(".", 2)[0]
-        if n.endswith("conv.bias") and prefix + ".norm.weight" in res[False]["grads"]:
-            # a conv bias in front of a batch-stat BN: its gradient is analytically zero, both
-            # paths return rounding noise — negligible against the weight gradient of the layer
-            wscale = float(res[False]["grads"][prefix + ".conv.weight"].abs().max())
-            assert float(res[True]["grads"][n].abs().max()) < 1e-3 * wscale, n
-            assert float(gref.abs().max()) < 1e-3 * wscale, n
-        else:
-            close(res[True]["grads"][n], gref, "grad " + n, 2e-3)
+        got = res[True]["grads"][n]
+        wname = n.rsplit(".", 1)[0] + ".weight"
+        if n.endswith(".bias") and wname in res[False]["grads"]:
+            # a bias whose effect is a per-channel constant removed by a LATER batch-stat BN (conv
+            # biases in front of a BN; the bare last conv of the first PointResNet, whose output
+            # reaches the KNN module's BN through the max-pool) has an analytically zero gradient:
+            # both paths return rounding noise, negligible against the layer's weight gradient
+            wscale = float(res[False]["grads"][wname].abs().max())
+            if float(gref.abs().max()) < 1e-3 * wscale:
+                assert float(got.abs().max()) < 1e-3 * wscale, n
+                continue
+        close(got, gref, "grad " + n, 2e-3)
