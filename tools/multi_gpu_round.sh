@@ -5,7 +5,7 @@ N=${1:-2}; TAG=${2:-r02}
 O=gpurun_out; mkdir -p $O
 nvidia-smi --query-gpu=index,name,clocks.max.sm --format=csv | head -10
 python -m pytest tests/test_gpu_nccl2.py -m gpu -q 2>&1 | tail -3 | tee $O/pytest_nccl2_$TAG.log
-for COLL in torch sonet; do
+for COLL in ${COLLS:-torch sonet}; do
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
      bench.py --gpus $N --steps 20 --warmup 3 --collective $COLL > $O/bench_${N}gpu_${COLL}_$TAG.json 2> $O/bench_${N}gpu_${COLL}_$TAG.err
   tail -2 $O/bench_${N}gpu_${COLL}_$TAG.err
