@@ -44,6 +44,10 @@ fi
 if [ "${LIST:-0}" = "1" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv \
      --log-file $O/launches_$TAG.csv python tools/profile_step.py --steps 4 > $O/ncu_list_$TAG.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv \
+     --log-file $O/launches_cfg4_$TAG.csv python tools/profile_step.py --steps 3 --task autoencoder --batch 32 > $O/ncu_list_cfg4_$TAG.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv \
+     --log-file $O/launches_cfg3_$TAG.csv python tools/profile_step.py --steps 3 --task segmenter --batch 32 --npts 1024 > $O/ncu_list_cfg3_$TAG.log 2>&1
 fi
 for K in ${NCU:-}; do
   N=$(echo $K | tr -c 'a-zA-Z0-9_\n' '_')
@@ -68,7 +72,7 @@ done
 for OP in ${OPS:-}; do python tools/profile_ops.py --op $OP --reps 6 2>&1 | tail -1; done
 if [ "${SANI:-0}" = "1" ]; then
   for TOOL in memcheck racecheck synccheck; do
-    timeout 1200 compute-sanitizer --tool $TOOL --print-limit 20 python tools/profile_step.py --steps 1 --batch 2 --npts 5000 \
+    timeout 1500 compute-sanitizer --tool $TOOL --print-limit 20 python tools/sanitize_all.py \
        > $O/sanitizer_${TOOL}_$TAG.log 2>&1
     echo "== $TOOL"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|done" $O/sanitizer_${TOOL}_$TAG.log | tail -3
   done
