@@ -32,7 +32,7 @@ namespace sonet {
 constexpr int CH_WARPS = 4;            // warps per CTA, each with its own 256-column chunk
 constexpr int CH_RN = 8;               // gt points per lane
 constexpr int CH_COLS = 32 * CH_RN;    // 256 columns per warp
-constexpr int CH_TM = 256;             // pred points per CTA tile
+constexpr int CH_TM = 128;             // pred points per CTA tile (256: 5.4 CTAs per SM, 80 us; see r02 summary)
 constexpr float CH_FAR = 1.0e30f;      // padding coordinate: (x - 1e30)^2 overflows to +inf
 
 // row_key [B,Mp] / col_key [B,N]: running minima as float bit patterns (init 0xFFFFFFFF).

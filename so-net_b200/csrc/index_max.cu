@@ -18,6 +18,7 @@
 //   * the masked gather that follows in the model (models/networks.py:185) is fused: the max
 //     value (or data[b,c,0] for empty nodes, as idx*mask_row_max gathers point 0) is emitted too.
 #include <algorithm>
+#include <cstdlib>
 #include <thread>
 #include <vector>
 
@@ -68,7 +69,7 @@ __device__ __forceinline__ void im_reduce_row(float* tval, IdxT* tidx, int lane,
 }
 
 // VEC path: N % 4 == 0 and 16B-aligned bases. blockDim = (NW + 1) * 32; warp NW is the producer.
-template <typename IdxT>
+template <typename IdxT, bool L2HINT>
 __global__ void __launch_bounds__((IM_MAX_WARPS + 1) * 32, 1)
     index_max_vec_kernel(const float* __restrict__ data, const int32_t* __restrict__ index, int B,
                          int C, int N, int K, int NW, int32_t* __restrict__ out_idx,
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__((IM_MAX_WARPS + 1) * 32, 1)
 #pragma unroll
       for (int u = 0; u < IM_UNROLL; ++u) {
         const int v = u * 32 + lane;
-        if (v < nvec_row) nxt[u] = ldg_stream_f4(row4 + v);
+        if (v < nvec_row) nxt[u] = L2HINT ? ldg_stream256_f4(row4 + v) : ldg_stream_f4(row4 + v);
       }
     }
     for (int ch = 0; ch < nch; ++ch) {
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__((IM_MAX_WARPS + 1) * 32, 1)
 #pragma unroll
             for (int u = 0; u < IM_UNROLL; ++u) {
               const int v = (g + 1) * GV + u * 32 + lane;
-              if (v < nvec_row) nxt[u] = ldg_stream_f4(row4 + v);
+              if (v < nvec_row) nxt[u] = L2HINT ? ldg_stream256_f4(row4 + v) : ldg_stream_f4(row4 + v);
             }
           }
 #pragma unroll
@@ -263,7 +264,12 @@ static int launch_index_max(const float* data, const int32_t* index, int B, int 
   const size_t smem = fixed + NW * per_warp;
   const int sms = sm_count();
   if (vec) {
-    auto kern = index_max_vec_kernel<IdxT>;
+    // SONET_IM_L2HINT=1: 256-byte L2 prefetch qualifier on the row loads (experiment switch)
+    static const bool hint = [] {
+      const char* e = getenv("SONET_IM_L2HINT");
+      return e != nullptr && e[0] == '1';
+    }();
+    auto kern = hint ? index_max_vec_kernel<IdxT, true> : index_max_vec_kernel<IdxT, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     const int groups = (C + NW - 1) / NW;
     const long long items = static_cast<long long>(B) * groups;
