@@ -44,6 +44,38 @@ __device__ __forceinline__ void im_update(float* tval, IdxT* tidx, int lane, int
   }
 }
 
+// Four consecutive points of one lane (a float4 of data, an int4 of node ids) folded into the table
+// with ALL FOUR table reads issued before the first write. im_update() alone forms a chain
+// LDS -> compare -> STS per element that the compiler cannot reorder (a later element of the same
+// node must see the earlier write), and the r02k ncu capture showed the kernel bound by exactly
+// that chain — 45 % of the stall samples on short-scoreboard (shared-memory results) against 8 %
+// on long-scoreboard (global loads). Same-node elements inside the quad are resolved in registers
+// by forwarding the running value (6 integer compares), so the semantics are unchanged: strict '>'
+// in ascending n keeps the first maximum.
+template <typename IdxT>
+__device__ __forceinline__ void im_update4(float* tval, IdxT* tidx, int lane, int K, int4 kk,
+                                           float4 d, int n) {
+  const unsigned kmax = static_cast<unsigned>(K - 1);
+  const int k0 = min(static_cast<unsigned>(kk.x), kmax), k1 = min(static_cast<unsigned>(kk.y), kmax),
+            k2 = min(static_cast<unsigned>(kk.z), kmax), k3 = min(static_cast<unsigned>(kk.w), kmax);
+  const int e0 = k0 * 32 + lane, e1 = k1 * 32 + lane, e2 = k2 * 32 + lane, e3 = k3 * 32 + lane;
+  const float t0 = tval[e0], t1 = tval[e1], t2 = tval[e2], t3 = tval[e3];
+  const bool u0 = d.x > t0;
+  const float c0 = u0 ? d.x : t0;
+  const float f1 = (k1 == k0) ? c0 : t1;
+  const bool u1 = d.y > f1;
+  const float c1 = u1 ? d.y : f1;
+  const float f2 = (k2 == k1) ? c1 : ((k2 == k0) ? c0 : t2);
+  const bool u2 = d.z > f2;
+  const float c2 = u2 ? d.z : f2;
+  const float f3 = (k3 == k2) ? c2 : ((k3 == k1) ? c1 : ((k3 == k0) ? c0 : t3));
+  const bool u3 = d.w > f3;
+  if (u0) { tval[e0] = d.x; tidx[e0] = static_cast<IdxT>(n); }
+  if (u1) { tval[e1] = d.y; tidx[e1] = static_cast<IdxT>(n + 1); }
+  if (u2) { tval[e2] = d.z; tidx[e2] = static_cast<IdxT>(n + 2); }
+  if (u3) { tval[e3] = d.w; tidx[e3] = static_cast<IdxT>(n + 3); }
+}
+
 // Cross-lane reduction of one finished row; also resets the table for the next row.
 template <typename IdxT>
 __device__ __forceinline__ void im_reduce_row(float* tval, IdxT* tidx, int lane, int K,
@@ -179,10 +211,7 @@ __global__ void __launch_bounds__((IM_MAX_WARPS + 1) * 32, 1)
             if (v < nvec_row) {
               const int4 kk = sidx4[v - ch * (IM_CHUNK / 4)];
               const int n = v << 2;
-              im_update<IdxT>(tval, tidx, lane, K, kk.x, d[u].x, n);
-              im_update<IdxT>(tval, tidx, lane, K, kk.y, d[u].y, n + 1);
-              im_update<IdxT>(tval, tidx, lane, K, kk.z, d[u].z, n + 2);
-              im_update<IdxT>(tval, tidx, lane, K, kk.w, d[u].w, n + 3);
+              im_update4<IdxT>(tval, tidx, lane, K, kk, d[u], n);
             }
           }
         }
