@@ -314,3 +314,68 @@ def test_cuda_graph_replay_matches_eager_and_tracks_changes():
     m.set_input(*[a[k] for k in keys])
     m.test_model()
     assert torch.allclose(m.score, want[0] + 1.0, atol=1e-5)
+
+
+def test_segmenter_training_gradients_reach_the_encoder():
+    """in train()/grad mode Segmenter.forward_nodes must gather the node-level feature
+    maps with a differentiable op (models/segmenter.py:96-98 uses torch.gather), so that the
+    encoder is trained through first_pn_out_masked_max, knn_feature_1 and final_pn_out — compared
+    against the reference call signature (per-point torch.gather by the caller)."""
+    from sonet_b200 import segmenter, synth
+    B, N = 4, 256
+    opt = synth.make_opt("segmenter", batch_size=B, input_pc_num=N)
+    st = build_states("segmenter", opt, seed=91)
+    inp = synth.synth_inputs(B, N, seed=91)
+    seg = (torch.arange(B * N).view(B, N) * 7) % 50
+    grads = {}
+    for mode in ("nodes", "reference_signature"):
+        m = segmenter.Model(_gpu_opt(opt))
+        m.encoder.load_state_dict(st["encoder"])
+        m.segmenter.load_state_dict(st["head"])
+        m.set_input(inp["pc"], inp["sn"], inp["label"], seg, inp["node"], inp["node_knn_I"])
+        m.encoder.train()
+        m.segmenter.train()
+        torch.manual_seed(0)
+        if mode == "nodes":
+            m.forward(is_train=True)
+        else:
+            enc = m.encoder
+            m.feature = enc(m.pc, m.sn, m.input_node, m.input_node_knn_I, True, None)
+            kN = enc.min_idx.shape[1]
+            idx = enc.min_idx.long().unsqueeze(1)
+            g = lambda t: torch.gather(t, 2, idx.expand(B, t.shape[1], kN))   # noqa: E731
+            m.score_segmenter = m.segmenter(enc.x_decentered, m.pc, enc.centers, m.sn, m.input_label,
+                                            enc.first_pn_out, g(enc.first_pn_out_masked_max),
+                                            g(enc.knn_feature_1), g(enc.final_pn_out), m.feature)
+        loss = m.softmax_segmenter(m.score_segmenter, m.seg)
+        m.encoder.zero_grad()
+        loss.backward()
+        grads[mode] = {n: p.grad.clone() for n, p in m.encoder.named_parameters() if p.grad is not None}
+    for name in ("final_pointnet.layers.1.conv.weight", "knnlayer.layers.1.conv.weight",
+                 "first_pointnet.layers.3.conv.weight"):
+        a, b = grads["nodes"][name], grads["reference_signature"][name]
+        assert float(b.abs().max()) > 0, name
+        err = float((a - b).abs().max()) / float(b.abs().max())
+        assert err <= 2e-3, "%s: %.3e" % (name, err)
+
+
+def test_pool_keys_survive_an_aborted_forward():
+    """a forward that dies between the fused pool launch and its finalisation must not
+    poison the next one (the keys are per-Encoder and re-initialised when left dirty)."""
+    from sonet_b200 import synth
+    opt = synth.make_opt("classifier", batch_size=2, input_pc_num=512)
+    st = build_states("classifier", opt, seed=93)
+    m = _classifier(opt, st)
+    keys = ("pc", "sn", "label", "node", "node_knn_I")
+    a, b = synth.synth_inputs(2, 512, seed=93), synth.synth_inputs(2, 512, seed=94)
+    m.set_input(*[b[k] for k in keys])
+    m.test_model()
+    want = m.score.clone()
+    m.set_input(*[a[k] for k in keys])
+    bad_knn = a["node_knn_I"][:, :, :4].contiguous()        # fewer than som_k columns
+    with pytest.raises(AssertionError):                      # the reference's own assertion (layers.py:330)
+        with torch.no_grad():
+            m.encoder(m.pc, m.sn, m.input_node, bad_knn.to(DEV))
+    m.set_input(*[b[k] for k in keys])
+    m.test_model()
+    assert torch.equal(m.score, want)
