@@ -691,12 +691,14 @@ static int launch_pointresnet_tc(const float* x, int Cin, int B, int P, const vo
     cl_env = e ? atoi(e) : 1;
     if (cl_env != 1 && cl_env != 2 && cl_env != 4) cl_env = 1;
   }
-  int cl = pool ? 1 : cl_env;
+  int cl = cl_env;
   const int sms = sm_count();
   while (cl > 1 && (tiles < cl || sms % cl != 0)) cl >>= 1;
   int grid = static_cast<int>(std::min<long long>(tiles, sms));
   grid -= grid % cl;
-  auto kern = pool ? pointresnet_tc_kernel<1, true>
+  auto kern = pool ? (cl == 4 ? pointresnet_tc_kernel<4, true>
+                              : (cl == 2 ? pointresnet_tc_kernel<2, true>
+                                         : pointresnet_tc_kernel<1, true>))
                    : (cl == 4 ? pointresnet_tc_kernel<4, false>
                               : (cl == 2 ? pointresnet_tc_kernel<2, false>
                                          : pointresnet_tc_kernel<1, false>));
