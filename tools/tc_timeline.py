@@ -29,10 +29,16 @@ with torch.no_grad():
         keys = torch.empty(64, 384, 64, dtype=torch.int32, device="cuda")
         _C.check(_C.lib().sonet_pool_keys_init(keys.data_ptr(), keys.numel(), None), "init")
         p0 = torch.empty(64, 384, device="cuda")
-        for _ in range(2):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for i in range(4):
+            if i == 3:
+                ev[0].record()
             _C.check(_C.lib().sonet_debug_pointresnet_tc_pool_timeline(
                 xs.data_ptr(), 6, 64, 15000, blob.data_ptr(), fpar.data_ptr(), ns.data_ptr(),
                 p0i.data_ptr(), 64, keys.data_ptr(), p0.data_ptr(), tl.data_ptr(), None), "timeline")
+        ev[1].record()
+        torch.cuda.synchronize()
+        EVENT_MS = ev[0].elapsed_time(ev[1])
     else:
         for _ in range(2):
             _C.check(_C.lib().sonet_debug_pointresnet_tc_timeline(
@@ -46,6 +52,11 @@ if starts:
     print("CTA 0: kernel %d cycles, %d tiles; first act0-ready at +%d, last at +%d (end +%d after it)"
           % (k1 - k0, len(starts), starts[0] - k0, starts[-1] - k0, k1 - starts[-1]))
     print("tile periods:", [b - a for a, b in zip(starts, starts[1:])])
+    if "EVENT_MS" in globals():
+        # SM cycles of CTA 0 (clock64) against the CUDA-event duration of the same launch: the SM
+        # clock the kernel actually ran at (nvidia-smi's 20 ms samples cannot see a 0.7 ms kernel)
+        print("launch: %.4f ms by CUDA events, %d SM cycles -> effective SM clock %.0f MHz"
+              % (EVENT_MS, k1 - k0, (k1 - k0) / EVENT_MS / 1e3))
 mma, epi = t[:32], t[32:64]
 t0 = min(v for v in (mma[:13] + epi[:14]) if v > 0)
 names_m = ["act0 ready", "L1 issued", "act1 ready", "L2 issued", "act2 ready"] + \
