@@ -159,7 +159,13 @@ int sonet_pointwise_tc_grouped_forward(const float* x, int C, int B, int P, cons
  *     scale2[0]=scale, scale2[1]=1/scale; scratch_bits: one uint32 of scratch.
  *   sonet_pointwise_tc_forward_dev: the generic tcgen05 layer with that blob (1/scale read from
  *     device memory): the forward GEMM y = W x + b and the dgrad GEMM dx = W^T dy of a training step.
- * The wgrad GEMM dW = dy x^T (contraction over points) is not part of this library yet. */
+ *   sonet_wgrad_tc_f32: the wgrad GEMM dW[co][ci] = sum_{b,p} dy[b,co,p] x[b,ci,p] on the same kernel:
+ *     dy is transposed to [K = B*P][Cout] and pre-scaled by a power of two (gradients are far below
+ *     fp16's normal range), x is packed as the weight operand with k = (b,p), K is split over
+ *     CTAs (splits) and reduced in a fixed order. Result dWT [Cin][Cout]. Device scratch: dyT
+ *     sonet_wgrad_kpad(B,P,splits)*Cout floats, blob sonet_wgrad_blob_bytes(Cin,Kpad) bytes,
+ *     part splits*Cin*Cout floats, small 8 floats. Needs Cout % 64 == 0.
+ *   sonet_absmax_scale_f32: scale2 = (s, 1/s), s the power of two with max|s*t| in [256,512). */
 int sonet_bn_partial_slots(int B, int C);
 int sonet_bn_train_forward_f32(const float* x, const float* gamma, const float* beta, int B, int C,
                                int P, float eps, int relu, double* partial, float* y,
@@ -174,8 +180,16 @@ int sonet_index_max_backward_f32(const float* grad_out, const int32_t* idx, int 
 int sonet_pointwise_tc_pack_device(const float* W, int Cout, int Cin, int transpose, void* blob,
                                    float* scale2, unsigned* scratch_bits, sonet_stream_t stream);
 int sonet_pointwise_tc_forward_dev(const float* x0, int C0, int B, int P, const void* blob,
-                                   const float* inv_scale_dev, const float* shift, int Cout, int relu,
-                                   float* out, sonet_stream_t stream);
+                                   const float* inv_scale_dev, const float* act_scale_dev,
+                                   const float* shift, int Cout, int relu, int splits, float* out,
+                                   float* scratch, sonet_stream_t stream);
+int sonet_absmax_scale_f32(const float* t, long long n, float* scale2, unsigned* scratch_bits,
+                           sonet_stream_t stream);
+long long sonet_wgrad_kpad(int B, int P, int splits);
+long long sonet_wgrad_blob_bytes(int Cin, long long Kpad);
+int sonet_wgrad_tc_f32(const float* dy, const float* x, int B, int Cout, int Cin, int P, int splits,
+                       float* dyT, void* blob, float* part, float* small, float* dWT,
+                       sonet_stream_t stream);
 
 /* ---- f-4: batch-SOM training --------------------------------------------------------------------
  * Replaces BatchSOM.batch_update / BatchSOM.optimize (util/som.py:295-366): T iterations of

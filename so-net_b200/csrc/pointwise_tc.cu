@@ -75,6 +75,9 @@ struct Dims {
   int P_out;     // point stride of `out` (= P unless scattering)
   const float* inv_ptr;     // non-null: 1 / weight pre-scale lives in device memory (train mode:
                             // the weights are packed on the device every step, csrc/train.cu)
+  const float* act_ptr;     // non-null: power-of-two pre-scale of the ACTIVATIONS (device memory),
+                            // applied before the fp16 hi/lo split — gradients are far below the
+                            // fp16 normal range; its inverse must be folded into *inv_ptr
   long long blob_gstride;   // bytes between the weight blobs of consecutive groups
   long long out_gstride;    // floats between the outputs of consecutive groups (0 when scattering)
   long long out_sstride;    // floats between the partial sums of consecutive K splits
@@ -245,6 +248,7 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
     // Each thread converts row m's 32 channels, which other threads copied: wait_group + a named
     // barrier before the read, another one before the tile is refilled with the next chunk.
     const uint32_t total = static_cast<uint32_t>(my_items) * d.kpi;
+    const float act_s = d.act_ptr != nullptr ? __ldg(d.act_ptr) : 1.f;
     float* stg = reinterpret_cast<float*>(smem + OFF_STG) + (half * 32) * TILE + m;
     const uint32_t stg_s = smem_u32(stg);
     auto issue = [&](uint32_t qq) {
@@ -359,8 +363,8 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float a = fminf(fmaxf(v[o * 8 + 2 * j], -65504.f), 65504.f);
-          const float c = fminf(fmaxf(v[o * 8 + 2 * j + 1], -65504.f), 65504.f);
+          const float a = fminf(fmaxf(v[o * 8 + 2 * j] * act_s, -65504.f), 65504.f);
+          const float c = fminf(fmaxf(v[o * 8 + 2 * j + 1] * act_s, -65504.f), 65504.f);
           const __half2 h = __floats2half2_rn(a, c);
           const float2 hf = __half22float2(h);
           const __half2 l = __floats2half2_rn(a - hf.x, c - hf.y);
@@ -593,6 +597,7 @@ static bool make_activation_map(CUtensorMap* m, const float* x, int B, int C, in
 struct TcExt {   // grouped / split-K / scatter launch options (defaults = the plain layer)
   int groups = 1, splits = 1, scat_w = 0, P_out = 0;
   const float* inv_ptr = nullptr;
+  const float* act_ptr = nullptr;
   long long blob_gstride = 0, out_gstride = 0, out_sstride = 0;
 };
 
@@ -631,6 +636,7 @@ static int launch_pointwise_tc(const float* x0, int C0, const float* x1, int C1,
   d.scat_w = ext.scat_w;
   d.P_out = ext.P_out > 0 ? ext.P_out : P;
   d.inv_ptr = ext.inv_ptr;
+  d.act_ptr = ext.act_ptr;
   d.blob_gstride = ext.blob_gstride;
   d.out_gstride = ext.out_gstride;
   d.out_sstride = ext.out_sstride;
@@ -727,15 +733,29 @@ extern "C" int sonet_pointwise_tc_grouped_forward(const float* x, int C, int B, 
 // Train-mode variant: the weight blob was packed on the device this step
 // (sonet_pointwise_tc_pack_device) and its 1/pre-scale is read from device memory.
 extern "C" int sonet_pointwise_tc_forward_dev(const float* x0, int C0, int B, int P, const void* blob,
-                                              const float* inv_scale_dev, const float* shift,
-                                              int Cout, int relu, float* out,
-                                              sonet_stream_t stream) {
+                                              const float* inv_scale_dev, const float* act_scale_dev,
+                                              const float* shift, int Cout, int relu, int splits,
+                                              float* out, float* scratch, sonet_stream_t stream) {
   using namespace sonet;
   SONET_REQUIRE(inv_scale_dev != nullptr, "pointwise_tc_forward_dev: null inv_scale pointer");
+  SONET_REQUIRE(splits >= 1 && (splits == 1 || scratch != nullptr),
+                "pointwise_tc_forward_dev: split-K needs scratch");
   TcExt e;
   e.inv_ptr = inv_scale_dev;
-  return launch_pointwise_tc(x0, C0, nullptr, 0, B, P, blob, 1.f, shift, Cout, relu, nullptr, nullptr,
-                             0, out, nullptr, stream, e);
+  e.act_ptr = act_scale_dev;
+  if (splits == 1)
+    return launch_pointwise_tc(x0, C0, nullptr, 0, B, P, blob, 1.f, shift, Cout, relu, nullptr,
+                               nullptr, 0, out, nullptr, stream, e);
+  const long long per_split = static_cast<long long>(B) * Cout * P;
+  e.splits = splits;
+  e.out_sstride = per_split;
+  int rc = launch_pointwise_tc(x0, C0, nullptr, 0, B, P, blob, 1.f, nullptr, Cout, 0, nullptr, nullptr,
+                               0, scratch, nullptr, stream, e);
+  if (rc) return rc;
+  const int grid = static_cast<int>(std::min<long long>((per_split + 255) / 256, 8LL * sm_count()));
+  splitk_reduce_kernel<<<grid, 256, 0, as_stream(stream)>>>(scratch, 1, splits, B, Cout, P, shift, relu,
+                                                            0, P, 0, out);
+  return check_launch("splitk_reduce");
 }
 
 extern "C" int sonet_debug_pointwise_tc_timeline(const float* x0, int C0, int B, int P,

@@ -223,6 +223,66 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- wgrad helpers ------------------------------------------------------------------------------------
+// dyT[k = b*P + p][co] = dy[b][co][p] * s  (s = scale2[0], a power of two): the "activation" operand
+// of the wgrad GEMM in the [K][rows] layout the generic tcgen05 layer consumes. 32x32 smem tiles.
+__global__ void __launch_bounds__(256)
+    transpose_scale_kernel(const float* __restrict__ dy, int C, int P, const float* __restrict__ scale2,
+                           float* __restrict__ dyT) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float s = scale2[0];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, p = p0 + tx;
+    tile[i][tx] = (c < C && p < P) ? dy[(static_cast<size_t>(b) * C + c) * P + p] * s : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int p = p0 + i, c = c0 + tx;
+    if (p < P && c < C) dyT[(static_cast<size_t>(b) * P + p) * C + c] = tile[tx][i];
+  }
+}
+// out2[0] = a[1] * b[1] (product of two inverse scales); out2[1] unused
+__global__ void inv_product_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                   float* __restrict__ out) {
+  out[0] = a[1] * b[1];
+}
+// x [B][Cin][P] as the "weight" matrix Wl[n = ci][k = b*P + p] of the wgrad GEMM, packed into the
+// tcgen05 blob layout (see tc_pack_device_kernel); K padded with zeros up to kch*64.
+__global__ void __launch_bounds__(256)
+    tc_pack_points_kernel(const float* __restrict__ x, int B, int Cin, int P,
+                          const float* __restrict__ scale2, unsigned char* __restrict__ blob, int cpad,
+                          int kch) {
+  const long long K = static_cast<long long>(B) * P;
+  const long long total = static_cast<long long>(cpad) * kch * 64;
+  const float sc = scale2[0];
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // consecutive threads -> consecutive k of one row n: coalesced reads of x along p
+    const long long k = t % (static_cast<long long>(kch) * 64);
+    const int n = static_cast<int>(t / (static_cast<long long>(kch) * 64));
+    const int nt = n / 256, r = n - nt * 256;
+    const int nw = min(256, cpad - nt * 256);
+    const long long kc = k >> 6;
+    const int hh = static_cast<int>((k >> 5) & 1), kk = static_cast<int>(k & 31);
+    float w = 0.f;
+    if (n < Cin && k < K) {
+      const long long b = k / P;
+      const int p = static_cast<int>(k - b * P);
+      w = x[(static_cast<size_t>(b) * Cin + n) * P + p] * sc;
+    }
+    const __half h = __float2half_rn(w);
+    const __half l = __float2half_rn(w - __half2float(h));
+    const size_t stage = static_cast<size_t>(nt) * 256 * kch * 64 * 4 +
+                         (static_cast<size_t>(kc) * 2 + hh) * nw * 32 * 4;
+    const uint32_t o = (r >> 3) * 512 + (kk >> 3) * 128 + (r & 7) * 16 + (kk & 7) * 2;
+    *reinterpret_cast<__half*>(blob + stage + o) = h;
+    *reinterpret_cast<__half*>(blob + stage + static_cast<size_t>(nw) * 32 * 2 + o) = l;
+  }
+}
+
 }  // namespace sonet
 
 static int bn_splits(int B, int C) {
@@ -306,4 +366,74 @@ extern "C" int sonet_pointwise_tc_pack_device(const float* W, int Cout, int Cin,
                           st>>>(W, Cout, Cin, transpose, scale2, static_cast<unsigned char*>(blob),
                                 cpad, kch);
   return check_launch("pointwise_tc_pack_device");
+}
+
+// power-of-two scale of a device tensor: scale2[0] = s with max|s*t| in [256,512), scale2[1] = 1/s
+extern "C" int sonet_absmax_scale_f32(const float* t, long long n, float* scale2, unsigned* scratch_bits,
+                                      sonet_stream_t stream) {
+  using namespace sonet;
+  SONET_REQUIRE(t && scale2 && scratch_bits && n >= 1, "absmax_scale: bad args");
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(scratch_bits, 0, sizeof(unsigned), st);
+  absmax_kernel<<<static_cast<unsigned>(std::min<long long>((n + 255) / 256, 2048)), 256, 0, st>>>(
+      t, n, scratch_bits);
+  scale_from_absmax_kernel<<<1, 1, 0, st>>>(scratch_bits, scale2);
+  return check_launch("absmax_scale");
+}
+
+extern "C" int sonet_pointwise_tc_forward_dev(const float* x0, int C0, int B, int P, const void* blob,
+                                              const float* inv_scale_dev, const float* act_scale_dev,
+                                              const float* shift, int Cout, int relu, int splits,
+                                              float* out, float* scratch, sonet_stream_t stream);
+
+// wgrad of a 1x1 convolution on tcgen05: dW[co][ci] = sum_{b,p} dy[b,co,p] * x[b,ci,p].
+// Written as the generic layer GEMM out[rows = co][n = ci] = sum_k A[k][co] * Wl[ci][k] with the
+// contraction index k = (b, p): A = dy transposed to [K][Cout] (and pre-scaled: gradients are far
+// below fp16's normal range), Wl = x packed as a weight blob, K split over CTAs with a
+// deterministic reduce. Result: dWT [Cin][Cout] (the caller views it transposed).
+// Scratch (device): dyT  Kpad*Cout floats, blob sonet_wgrad_blob_bytes(), part splits*Cin*Cout floats,
+// small: 8 floats + 2 uint32.
+extern "C" long long sonet_wgrad_kpad(int B, int P, int splits) {
+  const long long K = static_cast<long long>(B) * P;
+  const long long q = 64LL * splits;
+  return (K + q - 1) / q * q;
+}
+extern "C" long long sonet_wgrad_blob_bytes(int Cin, long long Kpad) {
+  const long long cpad = (Cin + 63) / 64 * 64;
+  return cpad * Kpad * 4;
+}
+extern "C" int sonet_wgrad_tc_f32(const float* dy, const float* x, int B, int Cout, int Cin, int P,
+                                  int splits, float* dyT, void* blob, float* part, float* small,
+                                  float* dWT, sonet_stream_t stream) {
+  using namespace sonet;
+  SONET_REQUIRE(dy && x && dyT && blob && part && small && dWT, "wgrad_tc: null pointer");
+  SONET_REQUIRE(B >= 1 && P >= 1 && Cout >= 64 && Cout % 64 == 0 && Cin >= 1 && splits >= 1 &&
+                    B <= 65535,
+                "wgrad_tc: needs Cout %% 64 == 0 (got Cout=%d, Cin=%d)", Cout, Cin);
+  cudaStream_t st = as_stream(stream);
+  const long long K = static_cast<long long>(B) * P;
+  const long long Kpad = sonet_wgrad_kpad(B, P, splits);
+  SONET_REQUIRE(Kpad < (1LL << 31), "wgrad_tc: too many points");
+  float* s_dy = small;            // [2]
+  float* s_x = small + 2;         // [2]
+  float* inv = small + 4;         // [1]
+  unsigned* bits = reinterpret_cast<unsigned*>(small + 6);
+  int rc = sonet_absmax_scale_f32(dy, static_cast<long long>(B) * Cout * P, s_dy, bits, stream);
+  if (rc) return rc;
+  rc = sonet_absmax_scale_f32(x, static_cast<long long>(B) * Cin * P, s_x, bits + 1, stream);
+  if (rc) return rc;
+  inv_product_kernel<<<1, 1, 0, st>>>(s_dy, s_x, inv);
+  if (Kpad > K)   // zero rows of the padded tail (the matching weight columns are packed as zeros too)
+    cudaMemsetAsync(dyT + K * Cout, 0, sizeof(float) * static_cast<size_t>(Kpad - K) * Cout, st);
+  transpose_scale_kernel<<<dim3((P + 31) / 32, (Cout + 31) / 32, B), 256, 0, st>>>(dy, Cout, P, s_dy, dyT);
+  const int cpad = (Cin + 63) / 64 * 64;
+  const int kch = static_cast<int>(Kpad / 64);
+  const long long total = static_cast<long long>(cpad) * Kpad;
+  tc_pack_points_kernel<<<static_cast<unsigned>(std::min<long long>((total + 255) / 256, 16384)), 256, 0,
+                          st>>>(x, B, Cin, P, s_x, static_cast<unsigned char*>(blob), cpad, kch);
+  rc = check_launch("wgrad_tc(prepare)");
+  if (rc) return rc;
+  // activations: dyT viewed as [B'=1][C'=Kpad][P'=Cout] (already scaled: no act pre-scale needed)
+  return sonet_pointwise_tc_forward_dev(dyT, static_cast<int>(Kpad), 1, Cout, blob, inv, nullptr, nullptr,
+                                        Cin, 0, splits, dWT, part, stream);
 }

@@ -3,8 +3,9 @@ Functions that the layer classes use in train() mode instead of the PyTorch comp
 conv1d -> batch_norm(training=True) -> relu and gather (models/layers.py:22-70, 282-296;
 models/networks.py:185).
 
-    ConvTC        y = W x + b and dx = W^T dy on the generic tcgen05 layer kernel (weights packed
-                  on the device each step); dW = dy x^T stays a cuBLAS fp32 GEMM for now
+    ConvTC        y = W x + b, dx = W^T dy AND dW = dy x^T on the generic tcgen05 layer kernel
+                  (weights / activations packed on the device each step; gradients pre-scaled by a
+                  power of two before the fp16 hi/lo split)
     BNActTrain    batch-statistics BatchNorm + ReLU, forward and backward, fused elementwise passes
                   and two-stage deterministic reductions
     IndexMaxGather  first_pn_out_masked_max = first_pn_out.gather(2, idx * mask_row_max) with the
@@ -80,12 +81,27 @@ def _pack_device(W, transpose):
     return blob, scale2
 
 
-def _tc_dev(x, blob, scale2, shift, cout):
+def _absmax_scale(t):
+    """(scale, 1/scale) device tensor: the power of two that puts max|t| into [256,512) — gradients
+    are far below fp16's normal range, so they are pre-scaled before the fp16 hi/lo split."""
+    dev = t.device
+    with torch.cuda.device(dev):
+        scale2 = torch.empty(2, dtype=torch.float32, device=dev)
+        bits = torch.empty(1, dtype=torch.int32, device=dev)
+        ops._call("sonet_absmax_scale_f32", _C.ptr(t), t.numel(), _C.ptr(scale2), _C.ptr(bits),
+                  ops._stream(t), kernels=2)
+    return scale2
+
+
+def _tc_dev(x, blob, inv, shift, cout, act_scale=None):
+    """Generic tcgen05 layer with a device-packed blob: inv (1-element device tensor) = the total
+    inverse pre-scale, act_scale (1-element) = activation pre-scale or None."""
     B, C, P = x.shape
     with torch.cuda.device(x.device):
         out = torch.empty((B, cout, P), dtype=torch.float32, device=x.device)
-        ops._call("sonet_pointwise_tc_forward_dev", _C.ptr(x), C, B, P, _C.ptr(blob),
-                  scale2[1:].data_ptr(), _C.ptr(shift), int(cout), 0, _C.ptr(out), ops._stream(x))
+        ops._call("sonet_pointwise_tc_forward_dev", _C.ptr(x), C, B, P, _C.ptr(blob), _C.ptr(inv),
+                  _C.ptr(act_scale), _C.ptr(shift), int(cout), 0, 1, _C.ptr(out), None,
+                  ops._stream(x))
     return out
 
 
@@ -93,15 +109,40 @@ def tc_eligible(cin, cout, rows):
     return cin >= 32 and cout >= 32 and rows >= 256
 
 
+def wgrad_tc(dy, x):
+    """dW [Cout,Cin] = sum_{b,p} dy[b,:,p] x[b,:,p]^T on tcgen05 (csrc/train.cu: sonet_wgrad_tc_f32)."""
+    B, Cout, P = dy.shape
+    Cin = x.shape[1]
+    lib = _C.lib()
+    base = ((Cout + 127) // 128) * (((Cin + 63) // 64 * 64 + 255) // 256)
+    splits = max(1, min(64, 296 // base, (B * P + 63) // 64))
+    Kpad = int(lib.sonet_wgrad_kpad(B, P, splits))
+    dev = dy.device
+    with torch.cuda.device(dev):
+        dyT = _scratch(dev, Kpad * Cout, torch.float32, _WGRAD_CACHE.setdefault("dyT", {}))
+        blob = _scratch(dev, int(lib.sonet_wgrad_blob_bytes(Cin, Kpad)), torch.uint8,
+                        _WGRAD_CACHE.setdefault("blob", {}))
+        part = _scratch(dev, splits * Cin * Cout, torch.float32, _WGRAD_CACHE.setdefault("part", {}))
+        small = torch.empty(8, dtype=torch.float32, device=dev)
+        dWT = torch.empty((Cin, Cout), dtype=torch.float32, device=dev)
+        ops._call("sonet_wgrad_tc_f32", _C.ptr(dy), _C.ptr(x), B, Cout, Cin, P, splits, _C.ptr(dyT),
+                  _C.ptr(blob), _C.ptr(part), _C.ptr(small), _C.ptr(dWT), ops._stream(dy), kernels=9)
+    return dWT.t()
+
+
+_WGRAD_CACHE = {}
+
+
 class ConvTC(torch.autograd.Function):
-    """x [B,Cin,P], W [Cout,Cin], b [Cout] or None -> W x + b."""
+    """x [B,Cin,P], W [Cout,Cin], b [Cout] or None -> W x + b. Forward, dgrad and wgrad all run on
+    the generic tcgen05 layer kernel (fp16 hi/lo split, fp32 accumulation)."""
 
     @staticmethod
     def forward(ctx, x, W, b):
         x = x.contiguous()
         Wc = W.contiguous()
         blob, scale2 = _pack_device(Wc, False)
-        y = _tc_dev(x, blob, scale2, None if b is None else b.contiguous(), Wc.shape[0])
+        y = _tc_dev(x, blob, scale2[1:], None if b is None else b.contiguous(), Wc.shape[0])
         ctx.save_for_backward(x, Wc)
         ctx.has_bias = b is not None
         return y
@@ -112,20 +153,26 @@ class ConvTC(torch.autograd.Function):
         dy = dy.contiguous()
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
-            blob, scale2 = _pack_device(W, True)                     # dgrad: dx = W^T dy (tcgen05)
-            dx = _tc_dev(dy, blob, scale2, None, W.shape[1])
+            blob, scale2 = _pack_device(W, True)                     # dgrad: dx = W^T dy
+            s_dy = _absmax_scale(dy)
+            inv = scale2[1:] * s_dy[1:]
+            dx = _tc_dev(dy, blob, inv, None, W.shape[1], act_scale=s_dy[:1])
         if ctx.needs_input_grad[1]:
-            # wgrad: contraction over (cloud, point) — cuBLAS fp32 (no TF32) until a tcgen05 NT kernel
-            # exists (include/sonet_b200.h, f-2 note)
-            prev = torch.backends.cuda.matmul.allow_tf32
-            torch.backends.cuda.matmul.allow_tf32 = False
-            try:
-                dW = torch.einsum("bop,bip->oi", dy, x)
-            finally:
-                torch.backends.cuda.matmul.allow_tf32 = prev
+            if W.shape[0] % 64 == 0 and W.shape[1] >= 16 and WGRAD_TC:
+                dW = wgrad_tc(dy, x)
+            else:                                                    # thin layers: cuBLAS fp32
+                prev = torch.backends.cuda.matmul.allow_tf32
+                torch.backends.cuda.matmul.allow_tf32 = False
+                try:
+                    dW = torch.einsum("bop,bip->oi", dy, x)
+                finally:
+                    torch.backends.cuda.matmul.allow_tf32 = prev
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum(dim=(0, 2))
         return dx, dW, db
+
+
+WGRAD_TC = True
 
 
 class IndexMaxGather(torch.autograd.Function):

@@ -65,6 +65,34 @@ def test_conv_tc_forward_dgrad_vs_torch(B, cin, cout, P):
         close(a, t.grad, n)
 
 
+@pytest.mark.parametrize("B,cin,cout,P,gscale", [(4, 64, 128, 1500, 1.0), (64, 387, 512, 576, 1e-6),
+                                                 (3, 320, 384, 1000, 3e-5), (2, 40, 64, 333, 1.0)])
+def test_wgrad_tc_vs_fp64(B, cin, cout, P, gscale):
+    """dW = sum_{b,p} dy x^T on tcgen05 (transpose + pre-scale of dy, x packed as the weight operand,
+    split-K with a fixed-order reduce) against fp64; gradients as small as 1e-6 keep full precision
+    because they are pre-scaled by a power of two before the fp16 split."""
+    from sonet_b200 import train_ops
+    g = torch.Generator().manual_seed(B + cin + P)
+    x = torch.randn(B, cin, P, generator=g).to(DEV)
+    dy = (torch.randn(B, cout, P, generator=g) * gscale).to(DEV)
+    got = train_ops.wgrad_tc(dy, x)
+    want = torch.einsum("bop,bip->oi", dy.double(), x.double())
+    close(got, want, "dW", 1e-4)
+    assert torch.equal(train_ops.wgrad_tc(dy, x), got)          # deterministic
+
+
+def test_dgrad_tiny_gradients_keep_precision():
+    from sonet_b200 import train_ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 128, 800, generator=g).to(DEV).requires_grad_(True)
+    W = (torch.randn(256, 128, generator=g) * 0.1).to(DEV).requires_grad_(True)
+    y = train_ops.ConvTC.apply(x, W, None)
+    w = (torch.randn(4, 256, 800, generator=g) * 1e-7).to(DEV)
+    (y * w).sum().backward()
+    want = torch.einsum("oi,bop->bip", W.detach().double(), w.double())
+    close(x.grad, want, "dx with 1e-7 gradients", 1e-4)
+
+
 def test_index_max_gather_backward_vs_torch_gather(oracle_mod):
     from sonet_b200 import train_ops
     rs = np.random.RandomState(4)
