@@ -7,4 +7,4 @@ include/sonet_b200.h. See DESIGN.md and INTEGRATION.md at the repository root.
 """
 from . import _C  # noqa: F401  (does not load the library until first use)
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
