@@ -29,11 +29,18 @@ __global__ void __launch_bounds__(256)
     som_assign_kernel(const float* __restrict__ x, const float* __restrict__ node, int N, int M,
                       int32_t* __restrict__ idx32, int64_t* __restrict__ idx64,
                       int32_t* __restrict__ row_flag, int32_t* __restrict__ mask) {
-  __shared__ float4 snode[SOM_MAX_M];
+  // nodes NEGATED and packed two per register pair: p - n == p + (-n) bit for bit, and the packed
+  // add/mul (FADD2/FMUL2) round each half like the scalar ops (sums stay scalar: common.cuh)
+  __shared__ float2 snx[SOM_MAX_M / 2], sny[SOM_MAX_M / 2], snz[SOM_MAX_M / 2];
   const int b = blockIdx.y;
   const float* nb = node + static_cast<size_t>(b) * 3 * M;
-  for (int m = threadIdx.x; m < M; m += blockDim.x)
-    snode[m] = make_float4(nb[m], nb[M + m], nb[2 * M + m], 0.f);
+  const int MP = (M + 1) >> 1;
+  for (int m2 = threadIdx.x; m2 < MP; m2 += blockDim.x) {
+    const int m0 = 2 * m2, m1 = min(2 * m2 + 1, M - 1);   // odd M: the last pair repeats its node
+    snx[m2] = make_float2(-nb[m0], -nb[m1]);
+    sny[m2] = make_float2(-nb[M + m0], -nb[M + m1]);
+    snz[m2] = make_float2(-nb[2 * M + m0], -nb[2 * M + m1]);
+  }
   __syncthreads();
 
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -42,6 +49,7 @@ __global__ void __launch_bounds__(256)
   const float* xb = x + static_cast<size_t>(b) * 3 * N;
   const int nl = live ? n : 0;
   const float px = xb[nl], py = xb[N + nl], pz = xb[2 * N + nl];
+  const float2 px2 = make_float2(px, px), py2 = make_float2(py, py), pz2 = make_float2(pz, pz);
 
   float bd[KK];
   int bi[KK];
@@ -50,12 +58,7 @@ __global__ void __launch_bounds__(256)
     bd[s] = __int_as_float(0x7f800000);  // +inf
     bi[s] = s;
   }
-#pragma unroll 4
-  for (int m = 0; m < M; ++m) {
-    const float4 q = snode[m];
-    const float dx = __fsub_rn(px, q.x), dy = __fsub_rn(py, q.y), dz = __fsub_rn(pz, q.z);
-    const float d =
-        __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  auto consider = [&](float d, int m) {
     if (d < bd[KK - 1]) {  // strict: on exact ties the earlier (lower) node index stays
       bd[KK - 1] = d;
       bi[KK - 1] = m;
@@ -71,6 +74,12 @@ __global__ void __launch_bounds__(256)
         }
       }
     }
+  };
+#pragma unroll 2
+  for (int m2 = 0; m2 < MP; ++m2) {
+    const float2 d = sqsum3_rn(add2_rn(px2, snx[m2]), add2_rn(py2, sny[m2]), add2_rn(pz2, snz[m2]));
+    consider(d.x, 2 * m2);
+    if (2 * m2 + 1 < M) consider(d.y, 2 * m2 + 1);
   }
   if (mask != nullptr) {
     // Fused dense one-hot mask (util/som.py:255-265), M % 32 == 0: the warp writes the KK rows of
