@@ -133,13 +133,20 @@ int sonet_comm_destroy(void* comm);
  *     leave most SMs idle while it streams K*256 weights alone. */
 int sonet_upconv_im2col_f32(const float* in, int B, int Cin, int H, int W, float* xcol,
                             sonet_stream_t stream);
+/* The im2col-free form for maps with H*W % 64 == 0 and Cin % 64 == 0: in [B,Cin,H,W] ->
+ * out [3][B][Cin][H*W], the input shifted horizontally by -1, 0, +1 (zeros at the row ends);
+ * sonet_pointwise_tc_grouped_forward(conv_w = W) then fetches tap (a,c) of parity (py,px) by TMA
+ * from block c-1+px+1 at point coordinate p + (a-1+py)*W (vertical shifts are coordinate offsets
+ * whose out-of-range part the TMA unit zero-fills): 3x the input is written instead of 16x. */
+int sonet_upconv_hshift_f32(const float* in, int B, int Cin, int H, int W, float* out,
+                            sonet_stream_t stream);
 int sonet_pointwise_tc_pack_groups(const float* W, int G, int Cout, int Cin, void* blob_host,
                                    float* inv_scale);
 int sonet_pointwise_tc_grouped_forward(const float* x, int C, int B, int P, const void* blob,
                                        long long blob_gstride, float inv_scale, const float* shift,
                                        int Cout, int relu, int groups, int splits, int scat_w,
-                                       int P_out, long long out_gstride, float* out, float* scratch,
-                                       sonet_stream_t stream);
+                                       int conv_w, int P_out, long long out_gstride, float* out,
+                                       float* scratch, sonet_stream_t stream);
 
 /* ---- f-2: train-mode kernels of the point-wise layers ---------------------------------------------
  * EquivariantLayer in train() mode = Conv1d(k=1) -> MyBatchNorm1d with BATCH statistics

@@ -73,6 +73,12 @@ struct Dims {
   int scat_w;    // > 0: group g = (py, px) parity of a x2 up-convolution over a [*, scat_w] map;
                  //      row p = i*W + j is stored at (2i+py)*2W + 2j+px of a [B, Cout, P_out] map
   int P_out;     // point stride of `out` (= P unless scattering)
+  int conv_w;    // > 0: up-convolution mode without im2col. x is [3*B, Cin, H*W] = the input shifted
+                 //      horizontally by -1, 0, +1 (csrc/upconv.cu); K chunk kc = (tap t = a*2+c,
+                 //      64-channel chunk): the TMA box is fetched from block c-1+px+1 at point
+                 //      coordinate p + (a-1+py)*W — vertical shifts are plain coordinate offsets,
+                 //      whose out-of-range part the TMA unit zero-fills
+  int cpt;       // 64-channel chunks per tap (= Cin / 64) in conv mode
   const float* inv_ptr;     // non-null: 1 / weight pre-scale lives in device memory (train mode:
                             // the weights are packed on the device every step, csrc/train.cu)
   const float* act_ptr;     // non-null: power-of-two pre-scale of the ACTIVATIONS (device memory),
@@ -268,13 +274,21 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
           for (int i = 0; i < 2; ++i) {
             const long long R = R0 + 64 * i;
             const int bl = static_cast<int>(R / d.P);
-            const int p = static_cast<int>(R - static_cast<long long>(bl) * d.P);
+            int p = static_cast<int>(R - static_cast<long long>(bl) * d.P);
             // rows past the group's last cloud must not read the next group: push them out of range
-            const int b = (bl < d.B) ? gb + bl : d.groups * d.B;
+            int b = (bl < d.B) ? gb + bl : d.groups * d.B;
+            int cc = kc * KCH;
+            if (d.conv_w > 0) {
+              const int tap = kc / d.cpt;
+              cc = (kc - tap * d.cpt) * KCH;
+              const int py = im.g >> 1, px = im.g & 1;
+              p += ((tap >> 1) - 1 + py) * d.conv_w;                 // vertical shift: OOB -> zeros
+              b = (bl < d.B) ? ((tap & 1) + px) * d.B + bl : 3 * d.B;   // horizontal-shift block 0..2
+            }
             asm volatile(
                 "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
                 "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(sdst + i * (STG_BYTES / 2)),
-                "l"(reinterpret_cast<uint64_t>(&xmap)), "r"(p), "r"(kc * KCH), "r"(b),
+                "l"(reinterpret_cast<uint64_t>(&xmap)), "r"(p), "r"(cc), "r"(b),
                 "r"(smem_u32(sfull))
                 : "memory");
           }
@@ -595,7 +609,7 @@ static bool make_activation_map(CUtensorMap* m, const float* x, int B, int C, in
 }
 
 struct TcExt {   // grouped / split-K / scatter launch options (defaults = the plain layer)
-  int groups = 1, splits = 1, scat_w = 0, P_out = 0;
+  int groups = 1, splits = 1, scat_w = 0, P_out = 0, conv_w = 0;
   const float* inv_ptr = nullptr;
   const float* act_ptr = nullptr;
   long long blob_gstride = 0, out_gstride = 0, out_sstride = 0;
@@ -617,7 +631,14 @@ static int launch_pointwise_tc(const float* x0, int C0, const float* x1, int C1,
   SONET_REQUIRE(aligned16(blob), "pointwise_tc: weight blob must be 16-byte aligned");
   Dims d;
   d.C0 = C0; d.C1 = C1; d.B = B; d.P = P; d.Cout = Cout; d.relu = relu; d.G = G;
-  d.cin_pad = (C0 + C1 + 15) / 16 * 16;
+  d.conv_w = ext.conv_w;
+  d.cpt = 1;
+  if (ext.conv_w > 0) {
+    SONET_REQUIRE(C1 == 0 && C0 % KCH == 0 && P % 64 == 0 && P % ext.conv_w == 0 && ext.groups == 4,
+                  "pointwise_tc: conv mode needs Cin %% 64 == 0, H*W %% 64 == 0 and the 4 parity groups");
+    d.cpt = C0 / KCH;
+  }
+  d.cin_pad = ext.conv_w > 0 ? 4 * C0 : (C0 + C1 + 15) / 16 * 16;
   d.kchunks = (d.cin_pad + KCH - 1) / KCH;
   d.ntiles = ((Cout + 63) / 64 * 64 + NT - 1) / NT;
   d.inv = inv_scale;
@@ -640,7 +661,12 @@ static int launch_pointwise_tc(const float* x0, int C0, const float* x1, int C1,
   d.blob_gstride = ext.blob_gstride;
   d.out_gstride = ext.out_gstride;
   d.out_sstride = ext.out_sstride;
-  d.tma = (!tma_off && C1 == 0 && make_activation_map(&xmap, x0, ext.groups * B, C0, P)) ? 1 : 0;
+  if (ext.conv_w > 0) {   // x = three horizontally shifted copies [3*B, Cin, P]; TMA is mandatory
+    d.tma = make_activation_map(&xmap, x0, 3 * B, C0, P) ? 1 : 0;
+    SONET_REQUIRE(d.tma, "pointwise_tc: conv mode needs the tensor-map TMA path");
+  } else {
+    d.tma = (!tma_off && C1 == 0 && make_activation_map(&xmap, x0, ext.groups * B, C0, P)) ? 1 : 0;
+  }
   const long long rows = static_cast<long long>(B) * P;
   d.row_tiles = static_cast<int>((rows + TILE - 1) / TILE);
   const long long items = static_cast<long long>(d.row_tiles) * d.ntiles * ext.groups * ext.splits;
@@ -697,8 +723,9 @@ extern "C" int sonet_pointwise_tc_grouped_forward(const float* x, int C, int B, 
                                                   const void* blob, long long blob_gstride,
                                                   float inv_scale, const float* shift, int Cout,
                                                   int relu, int groups, int splits, int scat_w,
-                                                  int P_out, long long out_gstride, float* out,
-                                                  float* scratch, sonet_stream_t stream) {
+                                                  int conv_w, int P_out, long long out_gstride,
+                                                  float* out, float* scratch,
+                                                  sonet_stream_t stream) {
   using namespace sonet;
   SONET_REQUIRE(groups >= 1 && splits >= 1 && scat_w >= 0, "pointwise_tc_grouped: bad group/split");
   SONET_REQUIRE(scat_w == 0 || (groups == 4 && P % scat_w == 0 && P_out == 4 * P && out_gstride == 0),
@@ -706,10 +733,12 @@ extern "C" int sonet_pointwise_tc_grouped_forward(const float* x, int C, int B, 
   SONET_REQUIRE(splits == 1 || scratch != nullptr, "pointwise_tc_grouped: split-K needs scratch");
   if (B == 0 || P == 0) return SONET_OK;
   if (P_out <= 0) P_out = P;
+  SONET_REQUIRE(conv_w == 0 || conv_w == scat_w, "pointwise_tc_grouped: conv_w must equal scat_w");
   TcExt e;
   e.groups = groups;
   e.splits = splits;
   e.blob_gstride = blob_gstride;
+  e.conv_w = conv_w;
   if (splits == 1) {
     e.scat_w = scat_w;
     e.P_out = P_out;

@@ -83,7 +83,39 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// The three horizontally shifted copies [3][B][Cin][H*W] (dx = -1, 0, +1, zero at the row ends)
+// that the conv mode of the grouped tcgen05 kernel reads instead of a 16x im2col: a vertical shift
+// is a plain offset of the TMA point coordinate (its out-of-range part is zero-filled by the TMA
+// unit), only the horizontal one wraps across image rows and has to be materialised.
+__global__ void __launch_bounds__(256)
+    upconv_hshift_kernel(const float* __restrict__ in, long long rows, int H, int W,
+                         float* __restrict__ out) {
+  const int HW = H * W;
+  const long long total = rows * HW;                         // rows = B * Cin
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(e % W);
+    const float v = __ldg(in + e);
+    out[total + e] = v;                                      // block 1: dx = 0
+    out[e] = (j > 0) ? __ldg(in + e - 1) : 0.f;              // block 0: reads column j-1
+    out[2 * total + e] = (j + 1 < W) ? __ldg(in + e + 1) : 0.f;   // block 2: column j+1
+  }
+}
+
 }  // namespace sonet
+
+extern "C" int sonet_upconv_hshift_f32(const float* in, int B, int Cin, int H, int W, float* out,
+                                       sonet_stream_t stream) {
+  using namespace sonet;
+  SONET_REQUIRE(B >= 0 && Cin >= 1 && H >= 1 && W >= 1, "upconv_hshift: bad dimension");
+  if (B == 0) return SONET_OK;
+  SONET_REQUIRE(in && out, "upconv_hshift: null pointer");
+  const long long rows = static_cast<long long>(B) * Cin;
+  const long long total = rows * H * W;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 16LL * sm_count()));
+  upconv_hshift_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, rows, H, W, out);
+  return check_launch("upconv_hshift");
+}
 
 extern "C" int sonet_upconv_im2col_f32(const float* in, int B, int Cin, int H, int W, float* xcol,
                                        sonet_stream_t stream) {

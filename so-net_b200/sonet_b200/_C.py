@@ -29,8 +29,9 @@ _SIGNATURES = {
     "sonet_pointwise_tc_pack_groups": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "sonet_pointwise_tc_grouped_forward": [c_void_p, c_int, c_int, c_int, c_void_p,
                                            ctypes.c_longlong, ctypes.c_float, c_void_p, c_int, c_int,
-                                           c_int, c_int, c_int, c_int, ctypes.c_longlong, c_void_p,
-                                           c_void_p, c_void_p],
+                                           c_int, c_int, c_int, c_int, c_int, ctypes.c_longlong,
+                                           c_void_p, c_void_p, c_void_p],
+    "sonet_upconv_hshift_f32": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "sonet_bn_partial_slots": [c_int, c_int],
     "sonet_bn_train_forward_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_float,
                                    c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],

@@ -404,13 +404,17 @@ class UpConv(nn.Module):
                                          pk["shift1"], 4 * Cout, relu, groups=1, splits=splits,
                                          scratch=scratch)
             return y.view(B, Cout, 2, 2)
-        xcol = ops.upconv_im2col(x)                                       # [4B, 4Cin, HW]
         P = H * W
         kch = (4 * Cin + 63) // 64
         splits = _pick_splits(kch, 4 * ((B * P + 127) // 128) * ((Cout + 255) // 256))
         scratch = self._scratch_for(4 * splits * B * Cout * P, x.device) if splits > 1 else None
-        y = ops.pointwise_tc_grouped(xcol, pk["blob4"], pk["per4"], pk["inv4"], pk["shift"], Cout,
-                                     relu, groups=4, splits=splits, scat_w=W, scratch=scratch)
+        # H*W % 64 == 0 and Cin % 64 == 0: no im2col — three horizontally shifted copies, the
+        # vertical shifts are TMA coordinate offsets inside the GEMM (3x the input instead of 16x)
+        conv = P % 64 == 0 and Cin % 64 == 0 and os.environ.get("SONET_UPCONV_IM2COL", "0") != "1"
+        xin = ops.upconv_hshift(x) if conv else ops.upconv_im2col(x)      # [3B,Cin,HW] | [4B,4Cin,HW]
+        y = ops.pointwise_tc_grouped(xin, pk["blob4"], pk["per4"], pk["inv4"], pk["shift"], Cout,
+                                     relu, groups=4, splits=splits, scat_w=W, scratch=scratch,
+                                     conv=conv)
         return y.view(B, Cout, 2 * H, 2 * W)
 
 

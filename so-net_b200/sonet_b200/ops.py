@@ -388,8 +388,19 @@ def upconv_im2col(x):
     return xcol
 
 
+def upconv_hshift(x):
+    """x [B,Cin,H,W] -> [3*B, Cin, H*W]: the input shifted horizontally by -1, 0, +1 (zeros at the
+    row ends) — the operand of the im2col-free up-convolution (csrc/upconv.cu)."""
+    _chk(x, "x", torch.float32)
+    B, Cin, H, W = x.shape
+    with torch.cuda.device(x.device):
+        out = torch.empty((3 * B, Cin, H * W), dtype=torch.float32, device=x.device)
+        _call("sonet_upconv_hshift_f32", _C.ptr(x), B, Cin, H, W, _C.ptr(out), _stream(x))
+    return out
+
+
 def pointwise_tc_grouped(x, blob, per_bytes, inv_scale, shift, cout, relu, groups, splits=1,
-                         scat_w=0, out=None, scratch=None):
+                         scat_w=0, out=None, scratch=None, conv=False):
     """Grouped tcgen05 layer: x [G*B, C, P], G weight blobs -> out. scat_w = W > 0: the four groups
     are the output parities of an up-convolution over [H, W] maps, interleaved into
     out [B, cout, 4*P]; otherwise out [G*B, cout, P]. splits > 1: K split through `scratch`."""
@@ -397,7 +408,7 @@ def pointwise_tc_grouped(x, blob, per_bytes, inv_scale, shift, cout, relu, group
     _chk(blob, "blob", torch.uint8)
     _chk(shift, "shift", torch.float32, optional=True)
     GB, C, P = x.shape
-    B = GB // groups
+    B = GB // (3 if conv else groups)       # conv mode: x holds the 3 horizontally shifted copies
     dev = x.device
     with torch.cuda.device(dev):
         if scat_w > 0:
@@ -412,7 +423,8 @@ def pointwise_tc_grouped(x, blob, per_bytes, inv_scale, shift, cout, relu, group
             scratch = torch.empty((groups * splits * B * cout * P,), dtype=torch.float32, device=dev)
         _call("sonet_pointwise_tc_grouped_forward", _C.ptr(x), C, B, P, _C.ptr(blob), int(per_bytes),
               float(inv_scale), _C.ptr(shift), int(cout), int(bool(relu)), int(groups), int(splits),
-              int(scat_w), int(P_out), int(gstride), _C.ptr(out), _C.ptr(scratch), _stream(x),
+              int(scat_w), int(scat_w) if conv else 0, int(P_out), int(gstride), _C.ptr(out),
+              _C.ptr(scratch), _stream(x),
               kernels=2 if splits > 1 else 1)
     return out
 
