@@ -11,6 +11,7 @@
 //   1. assignment (util/som.py:301-309): d = ((x-n)**2).sum(1) evaluated as (dx*dx+dy*dy)+dz*dz
 //      with separate roundings (no FMA) — bit-equal distances; torch.min -> first minimal index
 //      (strict '<' over ascending node index).
+//      Nodes are kept negated and packed two per register pair for the FADD2/FMUL2 forms.
 //   2. per-node statistics (:313-321): count and coordinate sums. The reference's torch.sum is a
 //      cascade summation (error ~1 ulp); sums here are accumulated in fp64 in a FIXED order and
 //      rounded once to fp32 — measured: a plain fp32 accumulation drifts by 1e-7 per sum, which
@@ -45,7 +46,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
   float4* snode = reinterpret_cast<float4*>(st_smem);                  // [M]
   float* smean = reinterpret_cast<float*>(snode + M);                  // [3][M]
   float* socc = smean + 3 * M;                                         // [M]
-  float* sw = socc + M;                                                // [M][M] when w_in_smem
+  float2* spk = reinterpret_cast<float2*>(socc + M);                   // [3][MP] negated node pairs
+  const int MP = (M + 1) >> 1;
+  float* sw = reinterpret_cast<float*>(spk + 3 * MP);                  // [M][M] when w_in_smem
   float* sx = sw + (w_in_smem ? M * M : 0);                            // [3][N] when x_in_smem
   unsigned char* sidx =
       reinterpret_cast<unsigned char*>(sx + (x_in_smem ? 3 * static_cast<size_t>(N) : 0));
@@ -55,6 +58,19 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
   const float* xg = x + static_cast<size_t>(b) * 3 * N;
   const float* ni = node_init + (node_init_batched ? static_cast<size_t>(b) * 3 * M : 0);
   for (int m = tid; m < M; m += ST_THREADS) snode[m] = make_float4(ni[m], ni[M + m], ni[2 * M + m], 0.f);
+  // packed, negated copies of the nodes for the assignment (p - n == p + (-n) bit for bit; FADD2 /
+  // FMUL2 round each half like the scalar ops, sums stay scalar — common.cuh); odd M: the last
+  // pair repeats its node and the duplicate is skipped
+  auto pack_nodes = [&]() {
+    for (int m2 = tid; m2 < MP; m2 += ST_THREADS) {
+      const float4 a = snode[2 * m2], b2 = snode[min(2 * m2 + 1, M - 1)];
+      spk[m2] = make_float2(-a.x, -b2.x);
+      spk[MP + m2] = make_float2(-a.y, -b2.y);
+      spk[2 * MP + m2] = make_float2(-a.z, -b2.z);
+    }
+  };
+  __syncthreads();
+  pack_nodes();
   if (x_in_smem)
     for (int i = tid; i < 3 * N; i += ST_THREADS) sx[i] = xg[i];
   const float* xs = x_in_smem ? sx : xg;
@@ -74,28 +90,48 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
       const float ax = xs[n0], ay = xs[N + n0], az = xs[2 * N + n0];
       const float bx = two ? xs[n1] : 0.f, by = two ? xs[N + n1] : 0.f,
                   bz = two ? xs[2 * N + n1] : 0.f;
+      const float2 ax2 = make_float2(ax, ax), ay2 = make_float2(ay, ay), az2 = make_float2(az, az);
+      const float2 bx2 = make_float2(bx, bx), by2 = make_float2(by, by), bz2 = make_float2(bz, bz);
       float da = __int_as_float(0x7f800000), db = da;
       int ia = 0, ib = 0;
-#pragma unroll 4
-      for (int m = 0; m < M; ++m) {
-        const float4 q = snode[m];
-        float dx = __fsub_rn(ax, q.x), dy = __fsub_rn(ay, q.y), dz = __fsub_rn(az, q.z);
-        float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        if (d < da) { da = d; ia = m; }
-        dx = __fsub_rn(bx, q.x); dy = __fsub_rn(by, q.y); dz = __fsub_rn(bz, q.z);
-        d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        if (d < db) { db = d; ib = m; }
+#pragma unroll 2
+      for (int m2 = 0; m2 < MP; ++m2) {
+        const float2 qx = spk[m2], qy = spk[MP + m2], qz = spk[2 * MP + m2];
+        const bool odd = 2 * m2 + 1 < M;
+        float2 d = sqsum3_rn(add2_rn(ax2, qx), add2_rn(ay2, qy), add2_rn(az2, qz));
+        if (d.x < da) { da = d.x; ia = 2 * m2; }
+        if (odd && d.y < da) { da = d.y; ia = 2 * m2 + 1; }
+        d = sqsum3_rn(add2_rn(bx2, qx), add2_rn(by2, qy), add2_rn(bz2, qz));
+        if (d.x < db) { db = d.x; ib = 2 * m2; }
+        if (odd && d.y < db) { db = d.y; ib = 2 * m2 + 1; }
       }
       sidx[n0] = static_cast<unsigned char>(ia);
       if (two) sidx[n1] = static_cast<unsigned char>(ib);
     }
     __syncthreads();
 
-    // ---- 2. per-node count / sums: warp per node, lanes stride the points, fixed order ---------
+    // ---- 2. per-node count / sums: warp per node, lanes stride the points, fixed order. The
+    // assignment bytes are scanned four at a time (one 32-bit shared load + a SIMD byte compare:
+    // 94 % of the words hold no point of the node and cost four instructions) ----
     for (int m = warp; m < M; m += ST_WARPS) {
       double s0 = 0.0, s1 = 0.0, s2 = 0.0;
       int cnt = 0;
-      for (int n = lane; n < N; n += 32) {
+      const uint32_t pat = static_cast<uint32_t>(m) * 0x01010101u;
+      const uint32_t* sidx4 = reinterpret_cast<const uint32_t*>(sidx);
+      const int nq = N >> 2;
+      for (int q = lane; q < nq; q += 32) {
+        uint32_t eq = __vcmpeq4(sidx4[q], pat);            // 0xff in every matching byte
+        while (eq != 0) {
+          const int byte = (__ffs(eq) - 1) >> 3;           // ascending point order inside the word
+          const int n = 4 * q + byte;
+          s0 += static_cast<double>(xs[n]);
+          s1 += static_cast<double>(xs[N + n]);
+          s2 += static_cast<double>(xs[2 * N + n]);
+          ++cnt;
+          eq &= ~(0xffu << (8 * byte));
+        }
+      }
+      for (int n = 4 * nq + lane; n < N; n += 32) {          // tail (N % 4 points)
         if (sidx[n] == m) {
           s0 += static_cast<double>(xs[n]);
           s1 += static_cast<double>(xs[N + n]);
@@ -145,6 +181,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
       p[c] = newv;
     }
     __syncthreads();
+    pack_nodes();
+    __syncthreads();
   }
 
   float* no = node_out + static_cast<size_t>(b) * 3 * M;
@@ -167,7 +205,7 @@ extern "C" int sonet_som_train(const float* x, const float* node_init, int node_
   if (B == 0) return SONET_OK;
   SONET_REQUIRE(x && node_init && node_out && (T == 0 || (weights && lr)), "som_train: null pointer");
   const int w_in_smem = (static_cast<size_t>(M) * M * sizeof(float) <= 64 * 1024) ? 1 : 0;
-  const size_t fixed = sizeof(float4) * M + sizeof(float) * 4 * M +
+  const size_t fixed = sizeof(float4) * M + sizeof(float) * 4 * M + sizeof(float2) * 3 * ((M + 1) / 2) +
                        (w_in_smem ? sizeof(float) * M * M : 0);
   const size_t with_x = fixed + sizeof(float) * 3 * static_cast<size_t>(N) + static_cast<size_t>(N) + 16;
   const size_t without_x = fixed + static_cast<size_t>(N) + 16;
