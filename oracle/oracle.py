@@ -269,23 +269,25 @@ def encoder_forward(st, opt, x, sn, node, node_knn_I, fast_pool=False, sorted_sl
     timing) instead of the single-thread restatement."""
     k = opt.k
     M = node.shape[2]
-    mask, mask_row_max, min_idx = query_topk(x, node, k, sorted_slots)      # networks.py:127
+    # index decisions always in fp32 (the reference's arithmetic); the value path follows x.dtype,
+    # so a float64 state + float64 inputs give the fp64 evaluation the precision tests compare with
+    mask, mask_row_max, min_idx = query_topk(x.float(), node.float(), k, sorted_slots)   # networks.py:127
     mask_row_sum = torch.sum(mask, dim=1)                                   # :128
-    maskf = mask.unsqueeze(1).float()
+    maskf = mask.unsqueeze(1).to(x.dtype)
     x_stack = torch.cat((x,) * k, dim=2)                                    # :132-137
     sn_stack = torch.cat((sn,) * k, dim=2)
     cluster_mean = torch.sum(x_stack.unsqueeze(3) * maskf, dim=2) / \
-        (mask_row_sum.unsqueeze(1).float() + 1e-5)                          # :140-142
+        (mask_row_sum.unsqueeze(1).to(x.dtype) + 1e-5)                      # :140-142
     som_node = cluster_mean
     centers = torch.sum(maskf * som_node.unsqueeze(2), dim=3)               # :168-169
     x_dec = x_stack - centers                                               # :171
     x_aug = torch.cat((x_dec, sn_stack), dim=1) if opt.surface_normal else x_dec
     first = pointresnet(x_aug, st, "first_pointnet")                        # :176
     if fast_pool:   # baseline timing; an int selects the thread count
-        gather_index = index_max_fast(first, min_idx.int(), M,
+        gather_index = index_max_fast(first.float(), min_idx.int(), M,
                                       None if fast_pool is True else int(fast_pool)).long()
     else:
-        gather_index = index_max(first, min_idx.int(), M).long()           # :181-184
+        gather_index = index_max(first.float().contiguous(), min_idx.int(), M).long()   # :181-184
     masked_max = first.gather(2, gather_index * mask_row_max.unsqueeze(1).long())  # :185
     out = dict(mask=mask, mask_row_max=mask_row_max, min_idx=min_idx, mask_row_sum=mask_row_sum,
                som_node=som_node, centers=centers, x_decentered=x_dec, first_pn_out=first,
@@ -315,7 +317,8 @@ def segmenter_forward(st, opt, enc, x, sn, label):
     kN = k * N
     idx = torch.max(enc["mask"], dim=2)[1].unsqueeze(1)                     # segmenter.py:90-91
     g = lambda t: torch.gather(t, 2, idx.expand(B, t.shape[1], kN))         # noqa: E731  :96-98
-    onehot = torch.zeros(B, 16).scatter_(1, label.unsqueeze(1), 1).unsqueeze(2).expand(B, 16, kN)
+    onehot = torch.zeros(B, 16, dtype=x.dtype).scatter_(1, label.unsqueeze(1), 1) \
+        .unsqueeze(2).expand(B, 16, kN)
     parts = [enc["x_decentered"], torch.cat((x,) * k, dim=2), enc["centers"]]
     if opt.surface_normal:
         parts.append(torch.cat((sn,) * k, dim=2))
