@@ -291,6 +291,15 @@ int sonet_gather_points_f32(const float* src, const int32_t* gidx, int B, int C,
 int sonet_kcopy_mean_f32(const float* in, int B, int C, int N, int k, float* out,
                          sonet_stream_t stream);
 
+/* Segmentation loss of the segmenter wrapper (models/losses.py:30-43 CrossEntropyLossSeg.forward as
+ * called by models/segmenter.py:129-131): mean (size_average=1) or sum over all points of
+ * -log_softmax(score[b,:,n])[target[b,n]]; score [B,C,N] f32, target [B,N] int64. Targets equal to
+ * -100 (NLLLoss's default ignore_index) do not count; any other out-of-range target yields NaN.
+ * scratch: sonet_seg_loss_scratch_bytes(B, N) bytes of device memory; loss: one float (device). */
+long long sonet_seg_loss_scratch_bytes(int B, int N);
+int sonet_seg_loss_f32(const float* score, const long long* target, int B, int C, int N,
+                       int size_average, void* scratch, float* loss, sonet_stream_t stream);
+
 /* ---- a-11: Chamfer distance ------------------------------------------------------------------------
  * Replaces ChamferLoss.forward (models/losses.py:237-290) including the Faiss IndexFlatL2
  * k=1 searches (losses.py:209-235) — exact brute force, direct differences, lowest index on ties.

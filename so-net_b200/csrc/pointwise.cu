@@ -457,6 +457,29 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// N % 4 == 0 and 16-byte aligned rows: one float4 of k copies per thread, 32-bit indexing per row
+__global__ void __launch_bounds__(256)
+    kcopy_mean_vec4_kernel(const float4* __restrict__ in, long long rows, int n4, int k,
+                           float4* __restrict__ out) {
+  const float w = (k == 2) ? 0.5f : (k == 3 ? (1.0f / 3.0f) : __fdiv_rn(1.0f, (float)k));
+  const long long total = rows * n4;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = t / n4;
+    const int n = static_cast<int>(t - r * n4);
+    const float4* p = in + r * k * n4 + n;
+    float4 s = ldg_stream_f4(p);
+    for (int i = 1; i < k; ++i) {
+      const float4 v = ldg_stream_f4(p + static_cast<size_t>(i) * n4);
+      s.x = __fadd_rn(s.x, v.x);
+      s.y = __fadd_rn(s.y, v.y);
+      s.z = __fadd_rn(s.z, v.z);
+      s.w = __fadd_rn(s.w, v.w);
+    }
+    out[t] = make_float4(__fmul_rn(w, s.x), __fmul_rn(w, s.y), __fmul_rn(w, s.z), __fmul_rn(w, s.w));
+  }
+}
+
 static inline int grid_for(long long total, int threads, int sms) {
   return static_cast<int>(std::max<long long>(
       1, std::min<long long>((total + threads - 1) / threads, 32LL * sms)));
@@ -604,6 +627,12 @@ extern "C" int sonet_kcopy_mean_f32(const float* in, int B, int C, int N, int k,
   const long long rows = static_cast<long long>(B) * C;
   if (rows * N == 0) return SONET_OK;
   SONET_REQUIRE(in && out, "kcopy_mean: null pointer");
+  if (N % 4 == 0 && aligned16(in) && aligned16(out)) {
+    const int n4 = N / 4;
+    kcopy_mean_vec4_kernel<<<grid_for(rows * n4, 256, sm_count()), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(in), rows, n4, k, reinterpret_cast<float4*>(out));
+    return check_launch("kcopy_mean");
+  }
   kcopy_mean_kernel<<<grid_for(rows * N, 256, sm_count()), 256, 0, as_stream(stream)>>>(in, rows, N, k,
                                                                                        out);
   return check_launch("kcopy_mean");

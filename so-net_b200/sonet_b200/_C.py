@@ -76,6 +76,9 @@ _SIGNATURES = {
     "sonet_gather_points_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                 c_void_p],
     "sonet_kcopy_mean_f32": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sonet_seg_loss_scratch_bytes": [c_int, c_int],
+    "sonet_seg_loss_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                           c_void_p],
     "sonet_chamfer_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "sonet_pointresnet_tc_blob_bytes": [],
@@ -116,6 +119,7 @@ _SIGNATURES = {
 _RESTYPE = {"sonet_last_error_string": ctypes.c_char_p, "sonet_version": ctypes.c_char_p,
             "sonet_pointwise_tc_blob_bytes": ctypes.c_longlong,
             "sonet_som_group_smem_bytes": ctypes.c_longlong,
+            "sonet_seg_loss_scratch_bytes": ctypes.c_longlong,
             "sonet_wgrad_kpad": ctypes.c_longlong, "sonet_wgrad_blob_bytes": ctypes.c_longlong}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

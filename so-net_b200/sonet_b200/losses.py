@@ -19,7 +19,8 @@ def robust_norm(var):
 
 class CrossEntropyLossSeg(nn.Module):
     """Per-point NLL over [B,classes,N] scores and [B,N] targets (models/losses.py:30-43).
-    Training/eval bookkeeping of the segmenter wrapper, plain PyTorch (not on the forward path)."""
+    Evaluation (no gradient asked for, fp32 CUDA scores, no class weights): one fused kernel +
+    a deterministic final sum (csrc/seg_loss.cu); training: PyTorch's differentiable op."""
 
     def __init__(self, weight=None, size_average=True):
         super().__init__()
@@ -27,6 +28,11 @@ class CrossEntropyLossSeg(nn.Module):
         self.reduction = 'mean' if size_average else 'sum'
 
     def forward(self, inputs, targets):
+        if (self.weight is None and inputs.is_cuda and inputs.dtype == torch.float32
+                and inputs.dim() == 3 and targets.dtype == torch.int64 and targets.is_cuda
+                and not (torch.is_grad_enabled() and inputs.requires_grad)):
+            return ops.seg_loss(inputs.contiguous(), targets.contiguous(),
+                                size_average=self.reduction == 'mean')
         return F.cross_entropy(inputs, targets, weight=self.weight, reduction=self.reduction)
 
 

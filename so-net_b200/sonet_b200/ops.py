@@ -291,6 +291,25 @@ def kcopy_mean(t, k):
     return out
 
 
+def seg_loss(score, target, size_average=True):
+    """score [B,C,N] f32, target [B,N] int64 -> scalar loss tensor (mean/sum of the per-point NLL
+    of log_softmax over the class axis, models/losses.py:30-43)."""
+    _chk(score, "score", torch.float32)
+    _chk(target, "target", torch.int64)
+    B, C, N = score.shape
+    if tuple(target.shape) != (B, N):
+        raise RuntimeError("seg_loss: target shape %s does not match scores %s"
+                           % (tuple(target.shape), tuple(score.shape)))
+    lib = _C.lib()
+    with torch.cuda.device(score.device):
+        scratch = torch.empty(int(lib.sonet_seg_loss_scratch_bytes(B, N)), dtype=torch.uint8,
+                              device=score.device)
+        loss = torch.empty((), dtype=torch.float32, device=score.device)
+        _call("sonet_seg_loss_f32", _C.ptr(score), _C.ptr(target), B, C, N, int(bool(size_average)),
+              _C.ptr(scratch), _C.ptr(loss), _stream(score), kernels=2)
+    return loss
+
+
 def chamfer(pred, gt, want_idx=False):
     """pred [B,3,Mp], gt [B,3,N] -> dict(loss [3], fwd_arr [B], bwd_arr [B], elem_fwd, elem_bwd,
     idx_fwd?, idx_bwd?)."""

@@ -215,6 +215,47 @@ def test_linear_rowmax_kcopy():
     assert torch.equal(ops.kcopy_mean(t.to(DEV), 3).cpu(), (1.0 / 3.0) * (sp[0] + sp[1] + sp[2]))
     sp = torch.split(t, 150, dim=2)
     assert torch.equal(ops.kcopy_mean(t.to(DEV), 2).cpu(), 0.5 * (sp[0] + sp[1]))
+    # scalar path (N % 4 != 0) and an offset (not 16-byte aligned) view
+    t = torch.from_numpy(rs.normal(size=(3, 5, 3 * 101)).astype(np.float32))
+    sp = torch.split(t, 101, dim=2)
+    assert torch.equal(ops.kcopy_mean(t.to(DEV), 3).cpu(), (1.0 / 3.0) * (sp[0] + sp[1] + sp[2]))
+
+
+def test_seg_loss_vs_torch():
+    """CrossEntropyLossSeg (models/losses.py:30-43): log_softmax over classes + NLL, mean / sum,
+    NLLLoss's default ignore_index, ragged N; against PyTorch in fp64."""
+    import torch.nn.functional as F
+    from sonet_b200 import losses, ops
+    rs = np.random.RandomState(21)
+    for B, C, N in ((32, 50, 1024), (3, 50, 1000), (2, 7, 33), (1, 1, 1)):
+        score = torch.from_numpy((rs.normal(size=(B, C, N)) * 4).astype(np.float32))
+        tgt = torch.from_numpy(rs.randint(0, C, size=(B, N)).astype(np.int64))
+        for avg in (True, False):
+            got = ops.seg_loss(score.to(DEV), tgt.to(DEV), size_average=avg)
+            want = F.cross_entropy(score.double(), tgt, reduction='mean' if avg else 'sum')
+            assert abs(float(got) - float(want)) <= 2e-6 * max(1.0, abs(float(want))), (B, C, N, avg)
+        # bit-reproducible
+        assert torch.equal(ops.seg_loss(score.to(DEV), tgt.to(DEV)), ops.seg_loss(score.to(DEV), tgt.to(DEV)))
+        if N > 4:
+            tgt2 = tgt.clone()
+            tgt2[:, ::3] = -100
+            got = ops.seg_loss(score.to(DEV), tgt2.to(DEV))
+            want = F.cross_entropy(score.double(), tgt2)
+            assert abs(float(got) - float(want)) <= 2e-6 * max(1.0, abs(float(want)))
+    # out-of-range target: loud (NaN), never a silent wrong number
+    bad = torch.full((1, 8), 9, dtype=torch.int64)
+    assert torch.isnan(ops.seg_loss(torch.zeros(1, 5, 8, device=DEV), bad.to(DEV)))
+    # the module takes the kernel path in eval and PyTorch's when a gradient is wanted
+    crit = losses.CrossEntropyLossSeg()
+    sc = score.to(DEV)
+    n0 = ops.LAUNCHES
+    with torch.no_grad():
+        a = crit(sc, tgt.to(DEV))
+    assert ops.LAUNCHES == n0 + 1
+    sc.requires_grad_(True)
+    b = crit(sc, tgt.to(DEV))
+    assert ops.LAUNCHES == n0 + 1 and b.requires_grad
+    assert abs(float(a) - float(b.detach())) <= 1e-5 * max(1.0, abs(float(b.detach())))
 
 
 def test_knn_gather_assemble_node_knn(oracle_mod):
