@@ -12,6 +12,8 @@
 // Also: MyLinear (small GEMV-like), row max, gathers used between the layers.
 #include <algorithm>
 
+#include <cuda_pipeline.h>
+
 #include "common.cuh"
 
 namespace sonet {
@@ -213,6 +215,136 @@ __global__ void __launch_bounds__(256)
   if (lane == 0) {
     float t = fmaf(s, scale ? scale[co] : 1.f, shift ? shift[co] : 0.f);
     out[warp_id] = relu ? fmaxf(t, 0.f) : t;
+  }
+}
+
+// ---- MyLinear, blocked: a block owns CT output channels for all clouds ------------------------------
+// The warp-per-output kernel above re-reads a weight row once per cloud (B x Cout x Cin loads through
+// L1: 22 us for [64,1024]->512). Here the CT weight rows of a block are staged in shared memory once,
+// each warp takes clouds warp, warp+8, ... two at a time (one LDS.128 of weights feeds two clouds'
+// FMAs), lanes stride the K axis in float4, and a butterfly reduces the 2*CT sums. Weight traffic:
+// once; activation traffic: (Cout/CT) x B x Cin from L2. Requires Cin % 4 == 0 and 16-byte aligned rows.
+template <int CT>
+__global__ void __launch_bounds__(256)
+    linear_block_kernel(const float* __restrict__ x, int B, int Cin, const float* __restrict__ W,
+                        const float* __restrict__ scale, const float* __restrict__ shift, int Cout,
+                        int relu, float* __restrict__ out) {
+  extern __shared__ __align__(16) float lb_w[];           // [CT][Cin]
+  const int co0 = blockIdx.x * CT;
+  const int c4 = Cin >> 2;
+  float4* sw = reinterpret_cast<float4*>(lb_w);
+  for (int i = threadIdx.x; i < CT * c4; i += 256) {
+    const int c = i / c4, k = i - c * c4;
+    sw[i] = (co0 + c < Cout) ? __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(co0 + c) * Cin) + k)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b0 = 2 * warp; b0 < B; b0 += 16) {
+    const bool two = b0 + 1 < B;
+    const float4* xa = reinterpret_cast<const float4*>(x + static_cast<size_t>(b0) * Cin);
+    const float4* xb = reinterpret_cast<const float4*>(x + static_cast<size_t>(two ? b0 + 1 : b0) * Cin);
+    float acc[2][CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) acc[0][c] = acc[1][c] = 0.f;
+#pragma unroll 2
+    for (int k = lane; k < c4; k += 32) {
+      const float4 va = __ldg(xa + k), vb = __ldg(xb + k);
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        const float4 w = sw[c * c4 + k];
+        acc[0][c] = fmaf(w.w, va.w, fmaf(w.z, va.z, fmaf(w.y, va.y, fmaf(w.x, va.x, acc[0][c]))));
+        acc[1][c] = fmaf(w.w, vb.w, fmaf(w.z, vb.z, fmaf(w.y, vb.y, fmaf(w.x, vb.x, acc[1][c]))));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        acc[0][c] += __shfl_xor_sync(0xffffffffu, acc[0][c], o);
+        acc[1][c] += __shfl_xor_sync(0xffffffffu, acc[1][c], o);
+      }
+    // lane c writes channel c of cloud b0, lane CT + c of cloud b0 + 1
+    if (lane < 2 * CT) {
+      const int h = lane / CT, c = lane - h * CT;
+      float v = 0.f;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int cc = 0; cc < CT; ++cc)
+          if (hh == h && cc == c) v = acc[hh][cc];
+      const int co = co0 + c;
+      if (co < Cout && (h == 0 || two)) {
+        const float t = fmaf(v, scale ? __ldg(scale + co) : 1.f, shift ? __ldg(shift + co) : 0.f);
+        out[static_cast<size_t>(b0 + h) * Cout + co] = relu ? fmaxf(t, 0.f) : t;
+      }
+    }
+  }
+}
+
+// ---- MyLinear, tiled: a block owns a [16 clouds x 16 channels] output tile ------------------------
+// The FC layers are latency-, not throughput-bound (67 MFLOP at [64,1024]->512): what matters is how
+// many dependent memory round trips a block makes. Here ALL operand bytes of the tile (16 rows of x,
+// 16 rows of W) are requested up front with 16-byte cp.async in four K stages, so the fetch latency is
+// paid once and the FMAs of stage s overlap the arrival of stages s+1..3. Thread (cloud, channel)
+// computes one output from shared memory: the x row is a broadcast, the 16 weight rows of a warp sit
+// 4 banks apart (row stride Cin + 4 floats) -> conflict-free LDS.128. Summation order depends on K
+// only (four interleaved partial sums, k ascending): results do not depend on the batch composition.
+constexpr int LT_B = 16, LT_C = 16, LT_STAGES = 4;
+
+__global__ void __launch_bounds__(256)
+    linear_tile_kernel(const float* __restrict__ x, int B, int Cin, const float* __restrict__ W,
+                       const float* __restrict__ scale, const float* __restrict__ shift, int Cout,
+                       int relu, float* __restrict__ out) {
+  extern __shared__ __align__(16) float lt_smem[];
+  const int c4 = Cin >> 2;               // float4 columns per row
+  const int ld4 = c4 + 1;                // padded row stride in float4
+  float4* xs = reinterpret_cast<float4*>(lt_smem);          // [LT_B][ld4]
+  float4* ws = xs + LT_B * ld4;                              // [LT_C][ld4]
+  const int b0 = blockIdx.y * LT_B, co0 = blockIdx.x * LT_C;
+  const int per = (c4 + LT_STAGES - 1) / LT_STAGES;
+  for (int s = 0; s < LT_STAGES; ++s) {
+    const int k0 = s * per, k1 = min(c4, k0 + per);
+    const int cols = max(0, k1 - k0);
+    for (int i = threadIdx.x; i < (LT_B + LT_C) * cols; i += 256) {
+      const int row = i / cols, k = k0 + (i - row * cols);
+      float4* dst = xs + row * ld4 + k;   // rows LT_B.. continue into ws
+      const float* src = nullptr;
+      if (row < LT_B) {
+        if (b0 + row < B) src = x + static_cast<size_t>(b0 + row) * Cin;
+      } else if (co0 + row - LT_B < Cout) {
+        src = W + static_cast<size_t>(co0 + row - LT_B) * Cin;
+      }
+      if (src != nullptr)
+        __pipeline_memcpy_async(dst, reinterpret_cast<const float4*>(src) + k, 16);
+      else
+        *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __pipeline_commit();
+  }
+  const int cloud = threadIdx.x >> 4, ch = threadIdx.x & 15;
+  const float4* xr = xs + cloud * ld4;
+  const float4* wr = ws + ch * ld4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int s = 0; s < LT_STAGES; ++s) {
+    __pipeline_wait_prior(LT_STAGES - 1 - s);
+    __syncthreads();
+    const int k0 = s * per, k1 = min(c4, k0 + per);
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) {
+      const float4 a = xr[k], w = wr[k];
+      acc.x = fmaf(a.x, w.x, acc.x);
+      acc.y = fmaf(a.y, w.y, acc.y);
+      acc.z = fmaf(a.z, w.z, acc.z);
+      acc.w = fmaf(a.w, w.w, acc.w);
+    }
+  }
+  const int b = b0 + cloud, co = co0 + ch;
+  if (b < B && co < Cout) {
+    const float v = (acc.x + acc.y) + (acc.z + acc.w);
+    const float t = fmaf(v, scale ? __ldg(scale + co) : 1.f, shift ? __ldg(shift + co) : 0.f);
+    out[static_cast<size_t>(b) * Cout + co] = relu ? fmaxf(t, 0.f) : t;
   }
 }
 
@@ -523,9 +655,38 @@ extern "C" int sonet_linear_f32(const float* x, int B, int Cin, const float* W, 
   SONET_REQUIRE(B >= 0 && Cin >= 1 && Cout >= 1, "linear: bad dimension");
   if (B == 0) return SONET_OK;
   SONET_REQUIRE(x && W && out, "linear: null pointer");
+  cudaStream_t st = as_stream(stream);
+  const size_t tile_smem = static_cast<size_t>(LT_B + LT_C) * (Cin / 4 + 1) * sizeof(float4);
+  if (Cin % 4 == 0 && aligned16(x) && aligned16(W) && tile_smem <= static_cast<size_t>(max_smem_optin())) {
+    cudaFuncSetAttribute(linear_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>(tile_smem));
+    dim3 grid((Cout + LT_C - 1) / LT_C, (B + LT_B - 1) / LT_B);
+    if (grid.y <= 65535) {
+      linear_tile_kernel<<<grid, 256, tile_smem, st>>>(x, B, Cin, W, scale, shift, Cout, relu, out);
+      return check_launch("linear");
+    }
+  }
+  if (Cin % 4 == 0 && aligned16(x) && aligned16(W)) {
+    // the widest channel tile that still fills the SMs and fits 48 KB of shared memory
+    const int sms = sm_count();
+    int ct = 4;
+    while (ct > 1 && ((Cout + ct - 1) / ct < (sms * 3) / 4 || static_cast<size_t>(ct) * Cin * 4 > 48 * 1024))
+      ct >>= 1;
+    const size_t smem = static_cast<size_t>(ct) * Cin * sizeof(float);
+    if (smem <= 48 * 1024) {
+      const int grid = (Cout + ct - 1) / ct;
+      if (ct == 4)
+        linear_block_kernel<4><<<grid, 256, smem, st>>>(x, B, Cin, W, scale, shift, Cout, relu, out);
+      else if (ct == 2)
+        linear_block_kernel<2><<<grid, 256, smem, st>>>(x, B, Cin, W, scale, shift, Cout, relu, out);
+      else
+        linear_block_kernel<1><<<grid, 256, smem, st>>>(x, B, Cin, W, scale, shift, Cout, relu, out);
+      return check_launch("linear");
+    }
+  }
   const long long total = static_cast<long long>(B) * Cout;
   const int grid = static_cast<int>((total * 32 + 255) / 256);
-  linear_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, B, Cin, W, scale, shift, Cout, relu, out);
+  linear_kernel<<<grid, 256, 0, st>>>(x, B, Cin, W, scale, shift, Cout, relu, out);
   return check_launch("linear");
 }
 

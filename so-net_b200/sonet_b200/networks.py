@@ -328,6 +328,12 @@ class Segmenter(nn.Module):
         return self._tail(out, k, self.opt.input_pc_num)
 
     # ---- B200 fast entry: node-level features + assignment, no per-point gathers ----------------
+    def _zero_idx(self, B, M, dev):
+        z = getattr(self, "_zidx", None)
+        if z is None or z.shape != (B, M) or z.device != dev:
+            z = self._zidx = torch.zeros((B, M), dtype=torch.int32, device=dev)
+        return z
+
     def _pack_layer1(self, n_pt_a, n_onehot, n_pp, n_node):
         """Split the folded layer-1 weight (transposed [Cin,1024]) by input-channel role."""
         l1 = self.layer1
@@ -340,13 +346,16 @@ class Segmenter(nn.Module):
             o2 = o1 + n_pp
             o3 = o2 + n_node
             w_point = torch.cat((w[0:o0], w[o1:o2]), dim=0).contiguous()     # coords | first_pn_out
-            w_node = torch.cat((w[o2:o3], w[o0:o1], w[o3:]), dim=0).contiguous()  # node|onehot|global
+            w_node = w[o2:o3].contiguous()                                    # node-level features
+            # per-cloud inputs (one-hot label | global feature): a [B,1040]x[1040,1024] fp32 GEMM
+            # whose result enters the node-level GEMM as a broadcast addend
+            w_cloud = torch.cat((w[o0:o1], w[o3:]), dim=0).t().contiguous()   # [1024, 1040]
             tc = None
             if os.environ.get("SONET_TC", "1") != "0":      # tcgen05 images of both halves
                 bp, ip = ops.pointwise_tc_pack(w_point.t().contiguous())
                 bn, inn = ops.pointwise_tc_pack(w_node.t().contiguous())
                 tc = (bp.to(w.device), ip, bn.to(w.device), inn)
-            self._l1_pack = (w_point, w_node, tc)
+            self._l1_pack = (w_point, w_node, w_cloud, tc)
             self._l1_key = key
         return self._l1_pack + (shift,)
 
@@ -356,9 +365,9 @@ class Segmenter(nn.Module):
         assignment min_idx_i32 [B,kN] instead of per-point gathered copies.
 
         Layer 1 is split algebraically: of its 3356 input channels only 396
-        vary per point; 1920 vary per node and 1040 per cloud. The node/cloud part is one small
-        GEMM over the M nodes whose result is gathered per point inside the epilogue of the
-        per-point GEMM — 6.85 instead of 25.2 GFLOP per cloud, and the [B,3356,kN] concat
+        vary per point; 1920 vary per node and 1040 per cloud. The cloud part is one [B,1040] fp32
+        GEMM, broadcast-added inside the node-level GEMM over the M nodes, whose result is in turn
+        gathered per point inside the epilogue of the per-point GEMM — 6.85 instead of 25.2 GFLOP per cloud, and the [B,3356,kN] concat
         (1.3 GB at B=32,N=1024) is never written.
         """
         if not (self.layer1.fast(first_pn_out) and self.opt.som_k >= 2):
@@ -379,22 +388,26 @@ class Segmenter(nn.Module):
         if use_sn:
             small.append(torch.cat((sn,) * k, dim=2))
         pt = torch.cat(small, dim=1).contiguous()                       # [B,12,kN]
-        w_point, w_node, tc, shift = self._pack_layer1(pt.shape[1], 16, first_pn_out.shape[1],
-                                                       node_first.shape[1] + node_knn.shape[1]
-                                                       + node_final.shape[1])
+        w_point, w_node, w_cloud, tc, shift = self._pack_layer1(
+            pt.shape[1], 16, first_pn_out.shape[1],
+            node_first.shape[1] + node_knn.shape[1] + node_final.shape[1])
         cloud = torch.cat((self._onehot(label, B, x.device), feature), dim=1)   # [B,1040]
-        node_in = torch.cat((node_first, node_knn, node_final,
-                             cloud.unsqueeze(2).expand(B, cloud.shape[1], M)), dim=1).contiguous()
+        cloud_add = ops.linear(cloud.contiguous(), w_cloud, None, None, False).unsqueeze(2)  # [B,1024,1]
+        zero_idx = self._zero_idx(B, M, x.device)
+        node_a = torch.cat((node_first, node_knn), dim=1).contiguous()   # [B,896,M]; node_final rides as x1
         relu1 = self.layer1.activation == 'relu'
         if tc is not None:
             bp, ip, bn, inn = tc
             cout = w_point.shape[1]
-            addend = ops.pointwise_layer_tc(node_in, bn, inn, None, cout, False)   # [B,1024,M]
+            addend = ops.pointwise_layer_tc(node_a, bn, inn, None, cout, False,
+                                            x1=node_final.contiguous(), addend=cloud_add,
+                                            gidx=zero_idx)                          # [B,1024,M]
             out1 = ops.pointwise_layer_tc(pt, bp, ip, shift, cout, relu1,
                                           x1=first_pn_out.contiguous(), addend=addend,
                                           gidx=min_idx_i32)
         else:
-            addend = ops.pointwise_layer(node_in, w_node, None, None, False)
+            addend = ops.pointwise_layer(node_a, w_node, None, None, False,
+                                         x1=node_final.contiguous(), addend=cloud_add, gidx=zero_idx)
             out1 = ops.pointwise_layer(pt, w_point, None, shift, relu1,
                                        x1=first_pn_out.contiguous(), addend=addend,
                                        gidx=min_idx_i32)

@@ -205,6 +205,17 @@ def test_linear_rowmax_kcopy():
     full = ops.linear(xb, W.to(DEV), None, shift.to(DEV), False)
     assert torch.equal(ops.linear(xb[:3].contiguous(), W.to(DEV), None, shift.to(DEV), False), full[:3])
     assert_close(full.cpu(), F.linear(xb.cpu(), W) + shift, "linear B=67", 2e-5)
+    assert torch.equal(ops.linear(xb[66:].contiguous(), W.to(DEV), None, shift.to(DEV), False), full[66:])
+    # channel tiles of 4 / 2 / 1, ragged Cout and B, folded scale, and the unaligned fallback
+    for B_, cin, cout in ((64, 1024, 512), (64, 512, 256), (33, 1040, 1024), (7, 256, 41), (1, 64, 3),
+                          (5, 1030, 17), (4, 12288, 8)):
+        x = torch.from_numpy(rs.normal(size=(B_, cin)).astype(np.float32))
+        W2 = torch.from_numpy((rs.normal(size=(cout, cin)) / np.sqrt(cin)).astype(np.float32))
+        sc = torch.from_numpy(rs.uniform(0.5, 2.0, size=cout).astype(np.float32))
+        sh = torch.from_numpy(rs.normal(size=cout).astype(np.float32))
+        want = F.relu(F.linear(x.double(), W2.double()) * sc.double() + sh.double())
+        got = ops.linear(x.to(DEV), W2.to(DEV), sc.to(DEV), sh.to(DEV), True)
+        assert_close(got, want, "linear %s" % ((B_, cin, cout),), 2e-5)
     for shape in ((3, 7, 64), (5, 3, 128), (2, 1033, 64), (2, 3, 40), (3, 5, 16)):
         t = torch.from_numpy(rs.normal(size=shape).astype(np.float32))
         assert torch.equal(ops.rowmax(t.to(DEV)).cpu(), t.max(dim=2)[0]), shape
