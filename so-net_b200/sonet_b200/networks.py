@@ -19,7 +19,7 @@ import torch.nn as nn
 
 from . import ops, som, train_ops
 from .layers import (EquivariantLayer, KNNModule, MyConv2d, MyLinear, PointNet, PointResNet,
-                     UpConv, _fast_ok)
+                     UpConv, _fast_ok, _pick_splits)
 
 
 def _bn_kwargs(opt):
@@ -353,8 +353,9 @@ class Segmenter(nn.Module):
             tc = None
             if os.environ.get("SONET_TC", "1") != "0":      # tcgen05 images of both halves
                 bp, ip = ops.pointwise_tc_pack(w_point.t().contiguous())
-                bn, inn = ops.pointwise_tc_pack(w_node.t().contiguous())
-                tc = (bp.to(w.device), ip, bn.to(w.device), inn)
+                # node-level GEMM: one launch of the grouped entry (K split to fill the SMs)
+                bn, pern, inn = ops.pointwise_tc_pack_groups(w_node.t().contiguous().unsqueeze(0))
+                tc = (bp.to(w.device), ip, bn.to(w.device), pern, inn)
             self._l1_pack = (w_point, w_node, w_cloud, tc)
             self._l1_key = key
         return self._l1_pack + (shift,)
@@ -393,21 +394,25 @@ class Segmenter(nn.Module):
             node_first.shape[1] + node_knn.shape[1] + node_final.shape[1])
         cloud = torch.cat((self._onehot(label, B, x.device), feature), dim=1)   # [B,1040]
         cloud_add = ops.linear(cloud.contiguous(), w_cloud, None, None, False).unsqueeze(2)  # [B,1024,1]
-        zero_idx = self._zero_idx(B, M, x.device)
-        node_a = torch.cat((node_first, node_knn), dim=1).contiguous()   # [B,896,M]; node_final rides as x1
         relu1 = self.layer1.activation == 'relu'
         if tc is not None:
-            bp, ip, bn, inn = tc
+            bp, ip, bn, pern, inn = tc
             cout = w_point.shape[1]
-            addend = ops.pointwise_layer_tc(node_a, bn, inn, None, cout, False,
-                                            x1=node_final.contiguous(), addend=cloud_add,
-                                            gidx=zero_idx)                          # [B,1024,M]
+            # [B,1920,M] -> [B,1024,M]: 16 row tiles x 4 column tiles would leave the GPU to 64
+            # CTAs that each walk all 30 K chunks; the K split brings it to one wave
+            node_in = torch.cat((node_first, node_knn, node_final), dim=1).contiguous()
+            kch = (node_in.shape[1] + 63) // 64
+            splits = _pick_splits(kch, ((B * M + 127) // 128) * ((cout + 255) // 256))
+            addend = ops.pointwise_tc_grouped(node_in, bn, pern, inn, None, cout, False, groups=1,
+                                              splits=splits) + cloud_add            # [B,1024,M]
             out1 = ops.pointwise_layer_tc(pt, bp, ip, shift, cout, relu1,
                                           x1=first_pn_out.contiguous(), addend=addend,
                                           gidx=min_idx_i32)
         else:
+            node_a = torch.cat((node_first, node_knn), dim=1).contiguous()
             addend = ops.pointwise_layer(node_a, w_node, None, None, False,
-                                         x1=node_final.contiguous(), addend=cloud_add, gidx=zero_idx)
+                                         x1=node_final.contiguous(), addend=cloud_add,
+                                         gidx=self._zero_idx(B, M, x.device))
             out1 = ops.pointwise_layer(pt, w_point, None, shift, relu1,
                                        x1=first_pn_out.contiguous(), addend=addend,
                                        gidx=min_idx_i32)
