@@ -63,7 +63,8 @@ struct Dims {
   int ntiles;    // out-channel tiles of <= 256 (each a multiple of 64)
   int cin_pad;   // Cin rounded up to 16
   int vec4;      // 16-byte activation fetch is legal (P % 4 == 0, 16-byte aligned bases)
-  int tma;       // activation chunks by tensor-map TMA (single source, P % 64 == 0)
+  int tma;       // activation chunks by tensor-map TMA (P % 64 == 0). Two sources: maps 1-3 (XMaps)
+  int h0;        // two-source TMA: channels of the chunk that straddles x0 | x1 coming from x0 (C0 % 64)
   float inv;     // 1 / weight pre-scale
   // ---- grouped / split-K / scatter extensions (the up-convolution decoder, csrc/upconv.cu) ----
   int groups;    // independent GEMMs sharing shapes: x is [groups*B, C, P], one weight blob each
@@ -113,12 +114,20 @@ __device__ __forceinline__ bool sonet_aligned16_dev(const void* p) {
   return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
 }
 
+// Tensor maps of the activation operand. 0: x0, box [64 p][64 c]; two sources (x0 | x1 along the
+// channel axis): 1: x1, box [64 p][64 c]; 2: x0, box [64 p][h0 c]; 3: x1, box [64 p][64 - h0 c] —
+// the one chunk that straddles the two tensors is fetched as two shorter boxes that land back to back
+// in the staging tile.
+struct XMaps {
+  CUtensorMap m[4];
+};
+
 __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
     pointwise_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
                         const unsigned char* __restrict__ blob, const float* __restrict__ shift,
                         const float* __restrict__ addend, const int32_t* __restrict__ gidx,
                         float* __restrict__ out, pwt::Dims d, long long* __restrict__ dbg,
-                        const __grid_constant__ CUtensorMap xmap) {
+                        const __grid_constant__ XMaps xm) {
   using namespace pwt;
 #define PW_TL(role, idx)                                                   \
   do {                                                                     \
@@ -285,12 +294,22 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
               p += ((tap >> 1) - 1 + py) * d.conv_w;                 // vertical shift: OOB -> zeros
               b = (bl < d.B) ? ((tap & 1) + px) * d.B + bl : 3 * d.B;   // horizontal-shift block 0..2
             }
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
-                "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(sdst + i * (STG_BYTES / 2)),
-                "l"(reinterpret_cast<uint64_t>(&xmap)), "r"(p), "r"(cc), "r"(b),
-                "r"(smem_u32(sfull))
-                : "memory");
+            auto box = [&](const CUtensorMap* mp, uint32_t dst, int c) {
+              asm volatile(
+                  "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+                  "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+                  "l"(reinterpret_cast<uint64_t>(mp)), "r"(p), "r"(c), "r"(b), "r"(smem_u32(sfull))
+                  : "memory");
+            };
+            const uint32_t dst = sdst + i * (STG_BYTES / 2);
+            if (d.C1 == 0 || cc + KCH <= d.C0) {
+              box(&xm.m[0], dst, cc);
+            } else if (cc < d.C0) {        // the straddling chunk: h0 channels of x0, then x1's first
+              box(&xm.m[2], dst, cc);
+              box(&xm.m[3], dst + static_cast<uint32_t>(d.h0) * 64 * 4, 0);
+            } else {
+              box(&xm.m[1], dst, cc - d.C0);
+            }
           }
         }
         return;
@@ -595,13 +614,13 @@ static TensorMapEncodeFn tensor_map_encoder() {
   return fn;
 }
 // 3-D map over x[B][C][P] fp32, box [64 p][64 c][1]; false when the layout does not qualify
-static bool make_activation_map(CUtensorMap* m, const float* x, int B, int C, int P) {
+static bool make_activation_map(CUtensorMap* m, const float* x, int B, int C, int P, int box_c = 64) {
   TensorMapEncodeFn enc = tensor_map_encoder();
   if (enc == nullptr || P % 64 != 0 || !sonet::aligned16(x)) return false;
   const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(P), static_cast<cuuint64_t>(C),
                               static_cast<cuuint64_t>(B)};
   const cuuint64_t gstr[2] = {static_cast<cuuint64_t>(P) * 4, static_cast<cuuint64_t>(C) * P * 4};
-  const cuuint32_t box[3] = {64, 64, 1};
+  const cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_c), 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), gdim, gstr, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -633,6 +652,7 @@ static int launch_pointwise_tc(const float* x0, int C0, const float* x1, int C1,
   d.C0 = C0; d.C1 = C1; d.B = B; d.P = P; d.Cout = Cout; d.relu = relu; d.G = G;
   d.conv_w = ext.conv_w;
   d.cpt = 1;
+  d.h0 = 0;
   if (ext.conv_w > 0) {
     SONET_REQUIRE(C1 == 0 && C0 % KCH == 0 && P % 64 == 0 && P % ext.conv_w == 0 && ext.groups == 4,
                   "pointwise_tc: conv mode needs Cin %% 64 == 0, H*W %% 64 == 0 and the 4 parity groups");
@@ -643,8 +663,9 @@ static int launch_pointwise_tc(const float* x0, int C0, const float* x1, int C1,
   d.ntiles = ((Cout + 63) / 64 * 64 + NT - 1) / NT;
   d.inv = inv_scale;
   d.vec4 = (P % 4 == 0) && aligned16(x0) && (C1 == 0 || aligned16(x1));
-  CUtensorMap xmap;
-  std::memset(&xmap, 0, sizeof(xmap));
+  XMaps xm;
+  std::memset(&xm, 0, sizeof(xm));
+  CUtensorMap& xmap = xm.m[0];
   static const bool tma_off = [] {
     const char* e = getenv("SONET_PW_TMA");
     return e != nullptr && e[0] == '0';
@@ -665,7 +686,19 @@ static int launch_pointwise_tc(const float* x0, int C0, const float* x1, int C1,
     d.tma = make_activation_map(&xmap, x0, 3 * B, C0, P) ? 1 : 0;
     SONET_REQUIRE(d.tma, "pointwise_tc: conv mode needs the tensor-map TMA path");
   } else {
-    d.tma = (!tma_off && C1 == 0 && make_activation_map(&xmap, x0, ext.groups * B, C0, P)) ? 1 : 0;
+    d.tma = (!tma_off && make_activation_map(&xmap, x0, ext.groups * B, C0, P)) ? 1 : 0;
+    if (d.tma && C1 > 0) {   // two sources: x1's map and the two short boxes of the straddling chunk
+      static const bool tma2_off = [] {
+        const char* e = getenv("SONET_PW_TMA2");
+        return e != nullptr && e[0] == '0';
+      }();
+      d.h0 = C0 % KCH;
+      bool ok = !tma2_off && ext.groups == 1 && make_activation_map(&xm.m[1], x1, B, C1, P);
+      if (ok && d.h0 > 0)
+        ok = make_activation_map(&xm.m[2], x0, B, C0, P, d.h0) &&
+             make_activation_map(&xm.m[3], x1, B, C1, P, KCH - d.h0);
+      d.tma = ok ? 1 : 0;
+    }
   }
   const long long rows = static_cast<long long>(B) * P;
   d.row_tiles = static_cast<int>((rows + TILE - 1) / TILE);
@@ -675,7 +708,7 @@ static int launch_pointwise_tc(const float* x0, int C0, const float* x1, int C1,
   cudaFuncSetAttribute(pointwise_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   const int grid = static_cast<int>(std::min<long long>(items, sm_count()));
   pointwise_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, as_stream(stream)>>>(
-      x0, x1, static_cast<const unsigned char*>(blob), shift, addend, gidx, out, d, dbg, xmap);
+      x0, x1, static_cast<const unsigned char*>(blob), shift, addend, gidx, out, d, dbg, xm);
   return check_launch("pointwise_tc");
 }
 

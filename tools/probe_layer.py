@@ -11,6 +11,7 @@ import torch  # noqa: E402
 from sonet_b200 import ops  # noqa: E402
 
 B, C, P, COUT = [int(v) for v in (sys.argv[1:5] if len(sys.argv) >= 5 else (32, 396, 3072, 1024))]
+C0 = int(sys.argv[5]) if len(sys.argv) >= 6 else 0      # > 0: two sources x0 [C0] + x1 [C - C0]
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(1)
 x = torch.randn(B, C, P, generator=g).to(dev)
@@ -39,7 +40,14 @@ def t(fn, reps=5):
 
 
 fl = 2.0 * C * COUT * B * P * 3
-for name, fn in (
+xa = x[:, :C0].contiguous() if C0 else None
+xb = x[:, C0:].contiguous() if C0 else None
+extra = ()
+if C0:
+    extra = (("two sources", lambda: ops.pointwise_layer_tc(xa, blob, inv, shift, COUT, True, x1=xb)),
+             ("two sources+addend", lambda: ops.pointwise_layer_tc(xa, blob, inv, shift, COUT, True, x1=xb,
+                                                                   addend=addend, gidx=gidx)))
+for name, fn in extra + (
         ("plain", lambda: ops.pointwise_layer_tc(x, blob, inv, shift, COUT, True)),
         ("addend random idx", lambda: ops.pointwise_layer_tc(x, blob, inv, shift, COUT, True,
                                                              addend=addend, gidx=gidx)),
