@@ -449,7 +449,6 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
       }
       const int cw = nw >> 1;                      // columns per warpgroup (multiple of 32)
       const int c_lo = h * cw;
-      const bool all_real = (nt * NT + nw) <= d.Cout;   // no padded output channels in this tile
       const bool sh_vec = shift != nullptr && sonet_aligned16_dev(shift);
       for (int c0 = c_lo; c0 < c_lo + cw; c0 += 32) {
         uint32_t v0[16], v1[16];
@@ -483,25 +482,59 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
         }
         if (valid) {
           float* o = out + obase + (static_cast<size_t>(b) * d.Cout + cg) * d.P_out + po;
-          // 16 columns at a time: the gathered addends (one per output element, segmenter layer 1)
-          // are all loaded before the first dependent add, like the shift values above
-          auto emit16 = [&](const uint32_t (&v)[16], int i0) {
-            float ad[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              ad[i] = (arow != nullptr && (all_real || cg + i0 + i < d.Cout))
-                          ? __ldg(arow + static_cast<size_t>(cg + i0 + i) * d.G)
-                          : 0.f;
+          const size_t ostep = static_cast<size_t>(d.P_out);
+          // The epilogue shares its sub-partitions with the converter warps: every instruction here
+          // is an issue slot the A-operand pipeline does not get (timeline: 2.3 k cycles per K chunk
+          // while no epilogue runs, 3.0 k while one does). The common case — all 32 channels real,
+          // no gathered addend — is therefore a separate warp-uniform path of FFMA, FMNMX, STG and a
+          // pointer bump per element (the general form below costs 19 instructions per element:
+          // 64-bit index multiplies, a bounds test and the addend select each time).
+          if (arow == nullptr && cg + 32 <= d.Cout) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              if (all_real || cg + i0 + i < d.Cout) {
-                const float y = fmaf(__uint_as_float(v[i]), inv_w, sh[i0 + i]) + ad[i];
-                o[static_cast<size_t>(i0 + i) * d.P_out] = fmaxf(y, floor_v);
-              }
+              *o = fmaxf(fmaf(__uint_as_float(v0[i]), inv_w, sh[i]), floor_v);
+              o += ostep;
             }
-          };
-          emit16(v0, 0);
-          emit16(v1, 16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              *o = fmaxf(fmaf(__uint_as_float(v1[i]), inv_w, sh[16 + i]), floor_v);
+              o += ostep;
+            }
+          } else if (cg + 32 <= d.Cout) {
+            // gathered addend (one per output element, segmenter layer 1): 16 loads in flight
+            // before the first dependent add
+            const float* ap = arow + static_cast<size_t>(cg) * d.G;
+            const size_t astep = static_cast<size_t>(d.G);
+            auto emit16 = [&](const uint32_t (&v)[16], int i0) {
+              float ad[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                ad[i] = __ldg(ap);
+                ap += astep;
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                *o = fmaxf(fmaf(__uint_as_float(v[i]), inv_w, sh[i0 + i]) + ad[i], floor_v);
+                o += ostep;
+              }
+            };
+            emit16(v0, 0);
+            emit16(v1, 16);
+          } else {
+            // ragged last channel group
+            auto emit16 = [&](const uint32_t (&v)[16], int i0) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                if (cg + i0 + i < d.Cout) {
+                  const float a = arow != nullptr ? __ldg(arow + static_cast<size_t>(cg + i0 + i) * d.G) : 0.f;
+                  const float y = fmaf(__uint_as_float(v[i]), inv_w, sh[i0 + i]) + a;
+                  o[static_cast<size_t>(i0 + i) * d.P_out] = fmaxf(y, floor_v);
+                }
+              }
+            };
+            emit16(v0, 0);
+            emit16(v1, 16);
+          }
         }
       }
       if (warp == 4 && it < 4) PW_TL(3, 2 * it + 1);
