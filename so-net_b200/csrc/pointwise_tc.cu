@@ -267,6 +267,10 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
     float* stg = reinterpret_cast<float*>(smem + OFF_STG) + (half * 32) * TILE + m;
     const uint32_t stg_s = smem_u32(stg);
     auto issue = [&](uint32_t qq) {
+      // TMA mode: one thread issues the boxes, and only that thread pays for the item decode (its
+      // integer divisions were 8.5 % of the kernel's executed instructions when all 256 converter
+      // threads evaluated them per chunk)
+      if (d.tma && t != 0) return;
       const int it = qq / d.kpi;
       const Item im = decode_item(d, blockIdx.x + it * gridDim.x);
       const int kc = im.kc0 + (qq - it * d.kpi);
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
       if (d.tma) {
         // two [64 p][64 c] boxes; staging layout [box][c][64 p]. Rows past the last cloud give
         // b >= B (fully out of range): the box is zero-filled and still counts its bytes.
-        if (t == 0) {
+        {
           uint64_t* sfull = &stg_full[qq % NSTG];
           const uint32_t sdst = smem_u32(smem + OFF_STG) + (qq % NSTG) * STG_BYTES;
           mbar_arrive_expect_tx(sfull, STG_BYTES);
@@ -390,14 +394,18 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
       const uint32_t slot = qq % NSTAGE, use = qq / NSTAGE;
       if (use > 0) tc::mbar_wait_bounded(&empty_a[slot], (use - 1) & 1, 204);
       if (warp == 12 && qq < 16) PW_TL(2, 2 * qq);
+      if (d.act_ptr != nullptr) {        // train-mode gradient pre-scale (warp-uniform)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= act_s;
+      }
       unsigned char* a_hi = smem + OFF_A + slot * A_BYTES + (m >> 3) * 1024 + (m & 7) * 16;
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float a = fminf(fmaxf(v[o * 8 + 2 * j] * act_s, -65504.f), 65504.f);
-          const float c = fminf(fmaxf(v[o * 8 + 2 * j + 1] * act_s, -65504.f), 65504.f);
+          const float a = fminf(fmaxf(v[o * 8 + 2 * j], -65504.f), 65504.f);
+          const float c = fminf(fmaxf(v[o * 8 + 2 * j + 1], -65504.f), 65504.f);
           const __half2 h = __floats2half2_rn(a, c);
           const float2 hf = __half22float2(h);
           const __half2 l = __floats2half2_rn(a - hf.x, c - hf.y);
