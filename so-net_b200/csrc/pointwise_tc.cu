@@ -404,13 +404,11 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float a = fminf(fmaxf(v[o * 8 + 2 * j], -65504.f), 65504.f);
-          const float c = fminf(fmaxf(v[o * 8 + 2 * j + 1], -65504.f), 65504.f);
-          const __half2 h = __floats2half2_rn(a, c);
-          const float2 hf = __half22float2(h);
-          const __half2 l = __floats2half2_rn(a - hf.x, c - hf.y);
-          hi[j] = *reinterpret_cast<const uint32_t*>(&h);
-          lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+          // saturating conversions keep |hi|, |lo| inside the fp16 range without clamp instructions
+          const float a = v[o * 8 + 2 * j], c = v[o * 8 + 2 * j + 1];
+          hi[j] = tc::pack_f16x2_sat(a, c);
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[j]));
+          lo[j] = tc::pack_f16x2_sat(a - hf.x, c - hf.y);
         }
         const int oct = half * 4 + o;
         *reinterpret_cast<uint4*>(a_hi + oct * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);

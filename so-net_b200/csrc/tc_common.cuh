@@ -310,18 +310,25 @@ __device__ __forceinline__ void split16(const float (&x)[16], uint32_t (&out)[16
 
 // ---- fp16 hi/lo split (22 significant bits, vs 16 for bf16) ---------------------------------------
 // Same instruction kind (kind::f16) and rate as bf16; operands must stay inside the fp16 range
-// (|x| <= 65504) — callers clamp activations and pre-scale weights by a power of two.
+// (|x| <= 65504) — the conversion saturates activations, weights are pre-scaled by a power of two.
 __host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N) {
   return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+// Two floats -> packed fp16 pair (lo = low half) with saturation to the largest finite fp16
+// (F2FP.SATFINITE: one instruction, where fminf/fmaxf clamps in front of a plain conversion cost
+// two to four more per pair). NaN stays NaN.
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ void split16_f16(const float (&x)[16], uint32_t (&out)[16]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const __half2 h = __floats2half2_rn(x[2 * j], x[2 * j + 1]);  // .x (low half) = even channel
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(x[2 * j] - hf.x, x[2 * j + 1] - hf.y);
-    out[j] = *reinterpret_cast<const uint32_t*>(&h);
-    out[8 + j] = *reinterpret_cast<const uint32_t*>(&l);
+    const uint32_t h = pack_f16x2_sat(x[2 * j], x[2 * j + 1]);   // low half = even channel
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h));
+    out[j] = h;
+    out[8 + j] = pack_f16x2_sat(x[2 * j] - hf.x, x[2 * j + 1] - hf.y);
   }
 }
 
