@@ -375,6 +375,7 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
       float v[32];
       if (d.tma) {
         tc::mbar_wait_bounded(&stg_full[qq % NSTG], (qq / NSTG) & 1, 206);   // both boxes landed
+        if (warp == 12 && qq >= 6 && qq < 16) PW_TL(2, 3 * (qq - 6));
         const float* sb = reinterpret_cast<const float*>(smem + OFF_STG + (qq % NSTG) * STG_BYTES) +
                           (m >> 6) * (KCH * 64) + (half * 32) * 64 + (m & 63);
 #pragma unroll
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
       }
       const uint32_t slot = qq % NSTAGE, use = qq / NSTAGE;
       if (use > 0) tc::mbar_wait_bounded(&empty_a[slot], (use - 1) & 1, 204);
-      if (warp == 12 && qq < 16) PW_TL(2, 2 * qq);
+      if (warp == 12 && qq >= 6 && qq < 16) PW_TL(2, 3 * (qq - 6) + 1);
       if (d.act_ptr != nullptr) {        // train-mode gradient pre-scale (warp-uniform)
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] *= act_s;
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(pwt::NUM_THREADS, 1)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_a[slot]);
-      if (warp == 12 && qq < 16) PW_TL(2, 2 * qq + 1);
+      if (warp == 12 && qq >= 6 && qq < 16) PW_TL(2, 3 * (qq - 6) + 2);
     }
   } else if (warp >= 4) {
     // ================= epilogue: two warpgroups split the item's columns =================

@@ -25,9 +25,9 @@ for kc in range(8):
     for j, n in enumerate(("full_w seen", "full_a seen", "issued+commit")):
         v = t[32 + 3 * kc + j]
         if v: ev.append((v - t0, "MMA  chunk %d %s" % (kc, n)))
-for q in range(16):
-    for j, n in enumerate(("slot free", "stored+arrive")):
-        v = t[64 + 2 * q + j]
+for q in range(6, 16):     # converter marks of chunks 6..15 (end of item 0, all of item 1)
+    for j, n in enumerate(("fp32 landed", "A slot free", "stored+arrive")):
+        v = t[64 + 3 * (q - 6) + j]
         if v: ev.append((v - t0, "CONV chunk %d %s" % (q, n)))
 for it in range(4):
     for j, n in enumerate(("d_full seen", "stored")):
