@@ -416,9 +416,12 @@ __global__ void __launch_bounds__(pm::NUM_THREADS, 1)
       }
     };
     auto store_group = [&](const uint32_t (&v)[16], int cbase) {   // lane = point: coalesced
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        cx_orow[static_cast<size_t>(cbase + i) * P] = fmaf(__uint_as_float(v[i]), inv3, sh3[cbase + i]);
+      float* o = cx_orow + static_cast<size_t>(cbase) * P;           // pointer bump, no 64-bit multiply
+#pragma unroll                                                       // per element (csrc/pointwise_tc.cu)
+      for (int i = 0; i < 16; ++i) {
+        *o = fmaf(__uint_as_float(v[i]), inv3, sh3[cbase + i]);
+        o += P;
+      }
     };
 
     uint32_t v0[16], v1[16], v2[16];    // this warp's 48 accumulator columns of one chunk
