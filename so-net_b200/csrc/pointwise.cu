@@ -453,14 +453,15 @@ __global__ void __launch_bounds__(256)
       ob[static_cast<size_t>(c) * MK + m * K + j] = __fsub_rn(cb[c * M + id], ctr);
     }
   }
-  // features: thread per (c, m, j)
-  const long long total = static_cast<long long>(C) * MK;
-  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
-       t += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int mj = static_cast<int>(t % MK);
-    const int c = static_cast<int>(t / MK);
-    const int m = mj / K, j = mj - m * K;
-    int id = clamp_idx(ib[m * Kstride + j], M);
+  // features: thread per (c, m, j); 32-bit index arithmetic (the launcher checks C*M*K < 2^31 — the
+  // 64-bit division and modulo per element were what this loop spent its time on)
+  const uint32_t total = static_cast<uint32_t>(C) * MK;
+  const uint32_t uMK = static_cast<uint32_t>(MK), uK = static_cast<uint32_t>(K);
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const uint32_t c = t / uMK;
+    const uint32_t mj = t - c * uMK;
+    const uint32_t m = mj / uK, j = mj - m * uK;
+    const int id = clamp_idx(ib[m * Kstride + j], M);
     ob[static_cast<size_t>(3 + c) * MK + mj] = __ldg(fb + static_cast<size_t>(c) * M + id);
   }
 }
@@ -732,6 +733,7 @@ extern "C" int sonet_knn_assemble_f32(const float* coord, const float* feat, con
   if (B == 0) return SONET_OK;
   SONET_REQUIRE(coord && (feat || C == 0) && idx && center && x_aug, "knn_assemble: null pointer");
   const long long per_b = static_cast<long long>(C + 3) * M * K;
+  SONET_REQUIRE(per_b < (1LL << 31), "knn_assemble: C*M*K = %lld exceeds the 32-bit index range", per_b);
   dim3 grid(static_cast<unsigned>(std::max<long long>(1, std::min<long long>((per_b + 255) / 256, 64))), B);
   knn_assemble_kernel<<<grid, 256, 0, as_stream(stream)>>>(coord, feat, idx, C, M, K, Kstride,
                                                            center_type, center, x_aug);

@@ -24,20 +24,24 @@
 
 namespace sonet {
 
+// IT = uint32_t whenever the element count fits (the four divisions per element bound this kernel
+// when they were 64-bit ones)
+template <typename IT>
 __global__ void __launch_bounds__(256)
     upconv_im2col_kernel(const float* __restrict__ in, int B, int Cin, int H, int W,
                          float* __restrict__ xcol) {
   const int HW = H * W;
-  const long long per_g = static_cast<long long>(B) * 4 * Cin * HW;
-  const long long total = per_g * 4;
-  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const IT uHW = static_cast<IT>(HW), uK = static_cast<IT>(4 * Cin);
+  const IT per_g = static_cast<IT>(B) * uK * uHW;
+  const IT total = per_g * 4;
+  for (IT e = static_cast<IT>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+       e += static_cast<IT>(gridDim.x) * blockDim.x) {
     const int g = static_cast<int>(e / per_g);
-    long long r = e - g * per_g;
-    const int p = static_cast<int>(r % HW);
-    r /= HW;
-    const int k = static_cast<int>(r % (4 * Cin));
-    const int b = static_cast<int>(r / (4 * Cin));
+    IT r = e - g * per_g;
+    const IT q = r / uHW;
+    const int p = static_cast<int>(r - q * uHW);
+    const int b = static_cast<int>(q / uK);
+    const int k = static_cast<int>(q - static_cast<IT>(b) * uK);
     const int t = k / Cin, ci = k - t * Cin;
     const int i = p / W, j = p - i * W;
     const int y = i + (t >> 1) - 1 + (g >> 1), x = j + (t & 1) - 1 + (g & 1);
@@ -136,6 +140,9 @@ extern "C" int sonet_upconv_im2col_f32(const float* in, int B, int Cin, int H, i
     return check_launch("upconv_im2col");
   }
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 16LL * sm_count()));
-  upconv_im2col_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, B, Cin, H, W, xcol);
+  if (total < (1LL << 32))
+    upconv_im2col_kernel<uint32_t><<<grid, 256, 0, as_stream(stream)>>>(in, B, Cin, H, W, xcol);
+  else
+    upconv_im2col_kernel<unsigned long long><<<grid, 256, 0, as_stream(stream)>>>(in, B, Cin, H, W, xcol);
   return check_launch("upconv_im2col");
 }
