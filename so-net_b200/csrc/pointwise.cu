@@ -471,7 +471,10 @@ __global__ void __launch_bounds__(256)
 // [B,C,M] maxima are written once (first_pn_out_masked_max, an Encoder attribute) and gathered
 // from shared memory. CTA = (channel group, cloud); threads run over the M*K output columns, so
 // the inner loop has no divisions and its stores are coalesced.
-constexpr int KA_CPB = 8;        // channels per CTA
+constexpr int KA_CPB = 16;       // channels per CTA
+__device__ __forceinline__ bool sonet_aligned16_ptr(const void* p) {
+  return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
 constexpr int KA_MAX_MK = 2304;  // M*K positions cached per CTA
 
 __global__ void __launch_bounds__(256)
@@ -481,7 +484,7 @@ __global__ void __launch_bounds__(256)
                              float* __restrict__ masked_max, float* __restrict__ center,
                              float* __restrict__ x_aug) {
   __shared__ float vals[KA_CPB * 256];          // [KA_CPB][M], M <= 256
-  __shared__ uint16_t sid[KA_MAX_MK];
+  __shared__ __align__(16) uint16_t sid[KA_MAX_MK];
   const int b = blockIdx.y;
   const int MK = M * K;
   const int c0 = blockIdx.x * KA_CPB;
@@ -501,10 +504,26 @@ __global__ void __launch_bounds__(256)
   }
   __syncthreads();
   float* ob = x_aug + static_cast<size_t>(b) * (3 + C) * MK;
-  for (int cl = 0; cl < nc; ++cl) {
-    float* orow = ob + static_cast<size_t>(3 + c0 + cl) * MK;
-    const float* vrow = vals + cl * M;
-    for (int mj = threadIdx.x; mj < MK; mj += blockDim.x) orow[mj] = vrow[sid[mj]];
+  if ((MK & 3) == 0 && sonet_aligned16_ptr(ob)) {
+    // four output columns per thread: one 8-byte read of the neighbour ids, one 16-byte store
+    const int MK4 = MK >> 2;
+    for (int t = threadIdx.x; t < nc * MK4; t += blockDim.x) {
+      const int cl = t / MK4, q = t - cl * MK4;
+      const float* vrow = vals + cl * M;
+      const uint2 ids = *reinterpret_cast<const uint2*>(sid + 4 * q);
+      float4 v;
+      v.x = vrow[ids.x & 0xffffu];
+      v.y = vrow[ids.x >> 16];
+      v.z = vrow[ids.y & 0xffffu];
+      v.w = vrow[ids.y >> 16];
+      reinterpret_cast<float4*>(ob + static_cast<size_t>(3 + c0 + cl) * MK)[q] = v;
+    }
+  } else {
+    for (int cl = 0; cl < nc; ++cl) {
+      float* orow = ob + static_cast<size_t>(3 + c0 + cl) * MK;
+      const float* vrow = vals + cl * M;
+      for (int mj = threadIdx.x; mj < MK; mj += blockDim.x) orow[mj] = vrow[sid[mj]];
+    }
   }
   if (blockIdx.x == 0) {   // coordinates: thread per (c, m)
     const float* cb = coord + static_cast<size_t>(b) * 3 * M;
