@@ -54,7 +54,21 @@ def test_bad_arguments_return_error_codes(lib_built):
     assert rc == -1
     with pytest.raises(RuntimeError):
         _C.check(rc, "chamfer")
+    # entry points added in round 2: argument checks come before any CUDA call
+    assert lib.sonet_seg_loss_f32(None, None, 2, 50, 1024, 1, None, None, None) == -1
+    assert "null" in _C.last_error()
+    assert lib.sonet_seg_loss_f32(None, None, 0, 50, 1024, 1, None, None, None) == -1
+    assert lib.sonet_seg_loss_scratch_bytes(32, 1024) >= 32 * 4 * 12
+    assert lib.sonet_seg_loss_scratch_bytes(-1, 4) == -1
+    assert lib.sonet_linear_f32(None, 4, 0, None, None, None, 8, 0, None, None) == -1
+    assert lib.sonet_linear_f32(None, 4, 16, None, None, None, 8, 0, None, None) == -1
+    assert "null" in _C.last_error()
+    assert lib.sonet_som_train(None, None, 0, None, None, 4, 2, 100, 300, None, None, None) == -1
+    assert "M=300" in _C.last_error()
+    assert lib.sonet_pointwise_tc_grouped_forward(None, 64, 2, 64, None, 0, 1.0, None, 64, 1, 4, 2, 0, 0,
+                                                  64, 0, None, None, None) == -1      # split-K, no scratch
     # empty batches are a no-op success
+    assert lib.sonet_linear_f32(None, 0, 16, None, None, None, 8, 0, None, None) == 0
     assert lib.sonet_index_max_f32(None, None, 0, 4, 4, 8, None, None, None) == 0
     assert lib.sonet_pointwise_layer_f32(None, 4, None, 0, 0, 16, None, None, None, 8, 1, None,
                                          None, 0, None, None) == 0
